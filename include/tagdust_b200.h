@@ -99,7 +99,9 @@ typedef struct tdg_result {
 	const float*   f_score;       /* mb->f_score */
 	const float*   b_score;       /* mb->b_score */
 	const float*   r_score;       /* mb->r_score */
-	const int32_t* read_type;     /* ri->read_type (extract_reads, then dust) */
+	const int32_t* read_type;     /* ri->read_type after extract_reads AND dust_sequences */
+	const uint8_t* extracted;     /* 1 where extract_reads succeeded (make_extracted_read ran, :3325),
+	                                 even if dust later overwrote read_type */
 	const int32_t* barcode;       /* ri->barcode   (-1 if not set) */
 	const int32_t* fingerprint;   /* ri->fingerprint (-1 if not set) */
 	const uint8_t* labels;        /* ri->labels[0..len] at labels + r*label_stride */

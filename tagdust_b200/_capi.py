@@ -72,6 +72,7 @@ class ResultC(C.Structure):
         ("b_score", c_float_p),
         ("r_score", c_float_p),
         ("read_type", c_int32_p),
+        ("extracted", c_uint8_p),
         ("barcode", c_int32_p),
         ("fingerprint", c_int32_p),
         ("labels", c_uint8_p),

@@ -1,0 +1,110 @@
+// tdg_device.h -- structures shared by the host runtime (tdg_host.cpp) and the kernels
+// (tdg_kernels.cu).  Internal; the public surface is include/tagdust_b200.h.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace tdg {
+
+constexpr int kMaxSegments = 16;
+constexpr int kLogsumSize = 16000;
+// Decode kernels: one CTA per SM, kBlock reads in flight per CTA (thread-per-read).
+constexpr int kBlock = 512;
+// Label-DP kernel uses smaller CTAs (no 64 KB table in shared memory).
+constexpr int kDpBlock = 128;
+constexpr int kColRec = 12;    // floats per column record (3 x float4)
+constexpr int kEmitRec = 10;   // eM[5], eI[5]
+constexpr int kMaxSources = 4; // label-DP predecessor sources per HMM (structured form)
+
+// Column record layout (floats), see barcode_hmm.h:87-96 for the transition indices:
+//  0 MM  1 MI  2 MD  3 II | 4 IM  5 DD  6 DM  7 MSKIP | 8 ISKIP  9 sM  10 sI  11 live-mask (int bits)
+enum ColField { F_MM = 0, F_MI, F_MD, F_II, F_IM, F_DD, F_DM, F_MSKIP, F_ISKIP, F_SM, F_SI, F_LIVE };
+// live-mask bits: bit k set <=> field k is not -inf (term can contribute)
+#define TDG_LIVE(k) (1u << (k))
+
+#ifdef __CUDACC__
+#define TDG_HD __host__ __device__
+#else
+#define TDG_HD
+#endif
+
+// Liveness of the terms of the "standard" profile column pattern that
+// set_hmm_transition_parameters(len>=3, mean=-1, stdev=-1) produces (barcode_hmm.c:1787-1880)
+// together with B/F/S entry (silent_to_M at column 0 only, :4897-4921):
+//   col 0        : DD DM MSKIP ISKIP sI dead
+//   cols 1..n-3  : MSKIP ISKIP sM sI dead
+//   col n-2      : MD DD MSKIP ISKIP sM sI dead
+//   col n-1      : everything dead but MSKIP
+// The host only selects the STD code path when every term listed dead IS -inf in the model.
+TDG_HD constexpr bool std_live(int nc, int g, int field)
+{
+	if (g == nc - 1) return field == F_MSKIP;
+	if (field == F_MSKIP || field == F_ISKIP || field == F_SI) return false;
+	if (field == F_SM) return g == 0;
+	if (g == 0) return !(field == F_DD || field == F_DM);
+	if (g == nc - 2) return !(field == F_MD || field == F_DD);
+	return true;
+}
+
+struct SegInfo {
+	int32_t nh;        // HMMs in segment
+	int32_t nc;        // columns per HMM
+	int32_t colbase;   // first global column
+	int32_t hmmbase;   // first global HMM
+	float   skip;      // model->skip
+	int32_t skip_live; // skip != -inf
+	int32_t kind;      // code path: 0 generic (runtime live masks), 1 STD column pattern
+};
+
+// Everything a kernel needs that is not in the model blob (passed by value).
+struct KArgs {
+	// model
+	int32_t S, H, C;
+	SegInfo seg[kMaxSegments];
+	const float* model_blob;   // device: [colrec C*12][emit C*10]
+	int32_t model_floats;      // floats to stage into shared memory after the logsum table
+	const float* logsum_tab;   // device: 16000 floats, entries >= 15700 zeroed
+	float r_step;              // log(1 - 1/avg) as float   (barcode_hmm.c:4520)
+	float r_end;               // log(1/avg) as float       (:4523)
+	float bg[5];               // model[0]->background_nuc_frequency
+	// batch (wave) geometry
+	int32_t n_reads;           // reads in this wave
+	int32_t lmax;              // scratch positions per read
+	int32_t words;             // packed 32-bit words per read (8 codes each)
+	int32_t win_start;         // matchstart or 0
+	int32_t win_len;           // matchend - matchstart, or -1 = whole read
+	const uint32_t* seq;       // device: tile layout [tile][word][lane]
+	const int32_t* len;        // device: [read]
+	// scratch (slot-major, see DESIGN.md "HBM layout")
+	float2* bw;                // [cta][C*lmax][kBlock]  (Mb, Ib)
+	float*  sb;                // [cta][S*(lmax+2)][kBlock] silent_backward
+	float*  sf;                // [cta][S*(lmax+2)][kBlock] silent_forward
+	float*  post;              // [cta][lmax*H][kBlock] posterior matrix rows 1..L
+	float*  tp;                // [cta][H][kBlock] total_prob
+	uint8_t* path;             // [cta][lmax*H][kBlock]
+	// per-read outputs (device)
+	float* b_score; float* f_score; float* r_score; float* bar_prob; float* mapq;
+	int32_t* read_type; int32_t* barcode; int32_t* fingerprint; uint8_t* extracted;
+	uint8_t* labels; int32_t label_stride;
+	int32_t dust;              // param->dust, 0 = off
+	// label-DP tables (device)
+	const int32_t* dp_src;     // [H][kMaxSources] source code: >=0 single hmm index, <0 = -(segment+1), INT_MIN = none
+	const int32_t* hmm_label;  // [H] mb->label
+	const uint8_t* seg_type;   // [S]
+	const uint8_t* tmat;       // [H*H] 0/1 (generic label-DP fallback)
+	int32_t dp_structured;     // 1: dp_src describes T exactly
+	// extraction
+	float confidence_threshold; int32_t minlen; int32_t required_finger_len; int32_t do_extract;
+	int32_t want_labels;
+};
+
+struct LaunchCfg { int ctas; };
+
+// launchers (tdg_kernels.cu); all asynchronous on `stream`
+int launch_backward(const KArgs& a, bool store, int ctas, void* stream);
+int launch_forward(const KArgs& a, int ctas, void* stream);
+int launch_label(const KArgs& a, int ctas_decode, void* stream);
+int kernels_configure(int smem_bytes); // sets the dynamic shared memory attributes once per device
+size_t decode_smem_bytes(int model_floats);
+
+}  // namespace tdg

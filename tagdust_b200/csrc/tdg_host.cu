@@ -1,0 +1,830 @@
+// tdg_host.cu -- host runtime behind the C ABI of include/tagdust_b200.h.
+//
+// What it replaces in the reference: run_pHMM()'s thread fan-out and per-thread model copies
+// (barcode_hmm.c:1895-2029, copy_model_bag :5262-5382).  Instead of pthreads over static
+// slices it shards a batch contiguously over the GPUs of the context, stages reads in pinned
+// 4-bit packed tiles, and queues H2D -> kernels -> D2H per device on streams.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tagdust_b200.h"
+#include "tdg_device.h"
+
+using namespace tdg;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return code;
+}
+#define CK(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return fail(e_ == cudaErrorMemoryAllocation ? TDG_EMEM : TDG_ECUDA, "%s:%d %s -> %s", \
+			            __FILE__, __LINE__, #call, cudaGetErrorString(e_));                        \
+	} while (0)
+
+extern "C" const char* tdg_last_error(void) { return g_err.c_str(); }
+extern "C" const char* tdg_version(void) { return "tagdust_b200 0.1 (sm_100a; reference TagDust 2.33)"; }
+
+// ------------------------------------------------------------------------------------------
+// host numerics identical to misc.c:57-105 (same libm, same expressions)
+// ------------------------------------------------------------------------------------------
+static float g_tab[kLogsumSize];
+static std::once_flag g_tab_once;
+static void init_tab()
+{
+	std::call_once(g_tab_once, [] {
+		for (int i = 0; i < kLogsumSize; i++) g_tab[i] = (float)log(1. + exp((double)-i / 1000.0f));
+	});
+}
+static inline float p2s(float p) { return p == 0.0 ? -HUGE_VALF : (float)log((double)p); }
+extern "C" void tdg_logsum_table(float* out)
+{
+	init_tab();
+	memcpy(out, g_tab, sizeof g_tab);
+}
+extern "C" float tdg_logsum_host(float a, float b)
+{
+	init_tab();
+	const float mx = (a > b) ? a : b;
+	const float mn = (a < b) ? a : b;
+	return (mn == -HUGE_VAL || (mx - mn) >= 15.7f) ? mx : mx + g_tab[(int)((mx - mn) * 1000.0f)];
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct DeviceCtx {
+	int dev = 0;
+	int sms = 0;
+	int ctas = 0;  // persistent decode CTAs = SM count
+	cudaStream_t compute = nullptr;
+	float* d_tab = nullptr;
+	// scratch arena (grown on demand; kernels of one device are serialised on `compute`)
+	void* scratch = nullptr;
+	size_t scratch_bytes = 0;
+	size_t smem_optin = 0;
+	int configured_smem = 0;
+};
+
+struct tdg_context {
+	std::vector<DeviceCtx> devs;
+};
+
+extern "C" int tdg_device_count(const tdg_context* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+extern "C" int tdg_init(int n_devices, const int* device_ids, tdg_context** out)
+{
+	if (!out) return fail(TDG_EINVAL, "tdg_init: out is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		cudaGetLastError();
+		return fail(TDG_ENODEV, "no CUDA device available (%s); tagdust_b200 has no CPU fallback",
+		            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	}
+	if (n_devices <= 0) n_devices = count;
+	if (n_devices > count && !device_ids) return fail(TDG_EINVAL, "asked for %d devices, %d visible", n_devices, count);
+	init_tab();
+	auto* ctx = new tdg_context();
+	for (int k = 0; k < n_devices; k++) {
+		DeviceCtx d;
+		d.dev = device_ids ? device_ids[k] : k;
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, d.dev));
+		if (prop.major < 10) {
+			delete ctx;
+			return fail(TDG_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", d.dev, prop.major, prop.minor);
+		}
+		CK(cudaSetDevice(d.dev));
+		d.sms = prop.multiProcessorCount;
+		d.ctas = d.sms;
+		d.smem_optin = prop.sharedMemPerBlockOptin;
+		CK(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
+		CK(cudaMalloc(&d.d_tab, sizeof g_tab));
+		std::vector<float> t(g_tab, g_tab + kLogsumSize);
+		for (int i = 15700; i < kLogsumSize; i++) t[i] = 0.0f;  // see LS() in tdg_kernels.cu
+		CK(cudaMemcpy(d.d_tab, t.data(), sizeof g_tab, cudaMemcpyHostToDevice));
+		ctx->devs.push_back(d);
+	}
+	*out = ctx;
+	return TDG_OK;
+}
+
+extern "C" void tdg_shutdown(tdg_context* ctx)
+{
+	if (!ctx) return;
+	for (auto& d : ctx->devs) {
+		cudaSetDevice(d.dev);
+		cudaStreamSynchronize(d.compute);
+		if (d.scratch) cudaFree(d.scratch);
+		if (d.d_tab) cudaFree(d.d_tab);
+		cudaStreamDestroy(d.compute);
+	}
+	delete ctx;
+}
+
+static int ensure_scratch(DeviceCtx& d, size_t bytes)
+{
+	if (bytes <= d.scratch_bytes) return TDG_OK;
+	CK(cudaSetDevice(d.dev));
+	CK(cudaStreamSynchronize(d.compute));
+	if (d.scratch) CK(cudaFree(d.scratch));
+	d.scratch = nullptr;
+	d.scratch_bytes = 0;
+	CK(cudaMalloc(&d.scratch, bytes));
+	d.scratch_bytes = bytes;
+	return TDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+struct ModelDev {
+	float* blob = nullptr;
+	int32_t* dp_src = nullptr;
+	int32_t* hmm_label = nullptr;
+	uint8_t* seg_type = nullptr;
+	uint8_t* tmat = nullptr;
+};
+
+struct HostModel {  // derived, GPU independent
+	int S = 0, H = 0, C = 0, avg = 0;
+	std::vector<SegInfo> seg;
+	std::vector<float> blob;       // colrec C*12 then emit C*10
+	std::vector<int32_t> dp_src;   // H * kMaxSources
+	std::vector<int32_t> label;
+	std::vector<uint8_t> seg_type;
+	std::vector<uint8_t> tmat;
+	int dp_structured = 0;
+	int required_finger_len = 0;
+	float bg[5];
+	float r_step = 0, r_end = 0;
+	int dead_terms = 0, std_segments = 0;
+};
+
+static bool is_ninf(float v) { return std::isinf(v) && v < 0; }
+
+static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err)
+{
+	char buf[256];
+	if (!d) { err = "desc is NULL"; return TDG_EINVAL; }
+	const int S = d->num_segments, H = d->total_hmms, C = d->total_columns;
+	if (S < 1 || S > kMaxSegments) { snprintf(buf, sizeof buf, "num_segments %d out of range 1..%d", S, kMaxSegments); err = buf; return TDG_EINVAL; }
+	if (H < 1 || H > TDG_MAX_HMMS) { snprintf(buf, sizeof buf, "total_hmms %d out of range 1..%d", H, TDG_MAX_HMMS); err = buf; return TDG_EINVAL; }
+	if (d->average_raw_length < 1) { err = "average_raw_length < 1"; return TDG_EINVAL; }
+	hm.S = S; hm.H = H; hm.C = C; hm.avg = d->average_raw_length;
+	hm.seg.resize(S);
+	int cb = 0, hb = 0;
+	for (int s = 0; s < S; s++) {
+		SegInfo& g = hm.seg[s];
+		g.nh = d->seg_num_hmms[s]; g.nc = d->seg_num_cols[s];
+		if (g.nh < 1 || g.nc < 1 || g.nc > 64) { snprintf(buf, sizeof buf, "segment %d: %d HMMs x %d columns unsupported (columns 1..64)", s, g.nh, g.nc); err = buf; return TDG_EINVAL; }
+		g.colbase = cb; g.hmmbase = hb; g.skip = d->seg_skip[s]; g.skip_live = !is_ninf(g.skip); g.kind = 0;
+		cb += g.nh * g.nc; hb += g.nh;
+	}
+	if (cb != C || hb != H) { err = "total_columns / total_hmms inconsistent with the segment tables"; return TDG_EINVAL; }
+	hm.blob.assign((size_t)C * (kColRec + kEmitRec), 0.0f);
+	float* rec = hm.blob.data();
+	float* emit = rec + (size_t)C * kColRec;
+	for (int c = 0; c < C; c++) {
+		float* r = rec + (size_t)c * kColRec;
+		for (int k = 0; k < 9; k++) r[k] = d->transition[c * 9 + k];
+		r[F_SM] = d->silent_to_M[c];
+		r[F_SI] = d->silent_to_I[c];
+		uint32_t live = 0;
+		for (int k = 0; k < 11; k++) {
+			if (std::isnan(r[k]) || (std::isinf(r[k]) && r[k] > 0)) { err = "model contains NaN/+inf"; return TDG_EINVAL; }
+			if (!is_ninf(r[k])) live |= 1u << k; else hm.dead_terms++;
+		}
+		memcpy(&r[F_LIVE], &live, 4);
+		for (int k = 0; k < 5; k++) {
+			emit[(size_t)c * kEmitRec + k] = d->m_emit[c * 5 + k];
+			emit[(size_t)c * kEmitRec + 5 + k] = d->i_emit[c * 5 + k];
+		}
+	}
+	// STD pattern check per segment: every term the pattern calls dead must be -inf
+	for (int s = 0; s < S; s++) {
+		SegInfo& g = hm.seg[s];
+		if (g.nc < 3 || g.nc > 8) continue;
+		bool ok = true;
+		for (int f = 0; f < g.nh && ok; f++)
+			for (int col = 0; col < g.nc && ok; col++) {
+				const float* r = rec + (size_t)(g.colbase + f * g.nc + col) * kColRec;
+				for (int k = 0; k < 11; k++)
+					if (!std_live(g.nc, col, k) && !is_ninf(r[k])) { ok = false; break; }
+			}
+		if (ok) { g.kind = 1; hm.std_segments++; }
+	}
+	// labels, types
+	hm.label.assign(d->label, d->label + H);
+	hm.seg_type.assign((const uint8_t*)d->seg_type, (const uint8_t*)d->seg_type + S);
+	for (int s = 0; s < S; s++)
+		if (d->seg_type[s] == 'F') hm.required_finger_len += d->seg_num_cols[s];
+	for (int h = 0; h < H; h++) {
+		const int sg = d->label[h] & 0xFFFF;
+		if (sg < 0 || sg >= S) { err = "label[] names a segment out of range"; return TDG_EINVAL; }
+	}
+	// label-DP transition matrix -> byte matrix + structured source lists
+	hm.tmat.assign((size_t)H * H, 0);
+	bool binary = true;
+	for (int c = 0; c < H; c++)
+		for (int j = 0; j < H; j++) {
+			const float t = d->transition_matrix[c * H + j];
+			if (t == 1.0f) hm.tmat[(size_t)c * H + j] = 1;
+			else if (t != 0.0f) binary = false;
+		}
+	if (!binary) { err = "transition_matrix entries must be 0 or 1"; return TDG_EINVAL; }
+	hm.dp_src.assign((size_t)H * kMaxSources, INT_MIN);
+	hm.dp_structured = 1;
+	for (int j = 0; j < H; j++) {
+		if (!hm.tmat[(size_t)j * H + j]) hm.dp_structured = 0;  // reference always sets the diagonal
+		int k = 0, c = 0;
+		while (c < j) {
+			if (!hm.tmat[(size_t)c * H + j]) { c++; continue; }
+			// whole segment starting at c?
+			int s = -1;
+			for (int q = 0; q < S; q++) if (hm.seg[q].hmmbase == c) s = q;
+			bool whole = false;
+			if (s >= 0 && hm.seg[s].hmmbase + hm.seg[s].nh <= j) {
+				whole = true;
+				for (int f = 0; f < hm.seg[s].nh; f++) if (!hm.tmat[(size_t)(c + f) * H + j]) whole = false;
+			}
+			if (k >= kMaxSources) { hm.dp_structured = 0; break; }
+			if (whole) { hm.dp_src[(size_t)j * kMaxSources + k++] = -(s + 1); c += hm.seg[s].nh; }
+			else { hm.dp_src[(size_t)j * kMaxSources + k++] = c; c++; }
+		}
+	}
+	for (int k = 0; k < 5; k++) hm.bg[k] = d->background[k];
+	// random model constants (barcode_hmm.c:4520,4523): float argument, double log, float result
+	hm.r_step = p2s((float)(1.0 - (1.0 / (float)d->average_raw_length)));
+	hm.r_end = p2s((float)(1.0 / (float)d->average_raw_length));
+	return TDG_OK;
+}
+
+struct tdg_model {
+	tdg_context* ctx = nullptr;
+	HostModel hm;
+	int max_len = 0;
+	std::vector<ModelDev> dev;
+	size_t slot_bytes_full = 0, slot_bytes_bwd = 0;
+};
+
+extern "C" int tdg_model_validate(const tdg_model_desc* desc, char* errbuf, size_t errbuf_len)
+{
+	HostModel hm;
+	std::string err;
+	const int rc = derive_model(desc, hm, err);
+	if (errbuf && errbuf_len) {
+		if (rc != TDG_OK) snprintf(errbuf, errbuf_len, "%s", err.c_str());
+		else snprintf(errbuf, errbuf_len, "ok: S=%d H=%d C=%d dead_terms=%d std_segments=%d dp_structured=%d", hm.S, hm.H, hm.C,
+		              hm.dead_terms, hm.std_segments, hm.dp_structured);
+	}
+	if (rc != TDG_OK) g_err = err;
+	return rc;
+}
+
+template <class T>
+static int upload(T** dst, const std::vector<T>& v)
+{
+	CK(cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
+	if (!v.empty()) CK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	return TDG_OK;
+}
+
+extern "C" void tdg_model_destroy(tdg_model* m)
+{
+	if (!m) return;
+	for (size_t k = 0; k < m->dev.size(); k++) {
+		cudaSetDevice(m->ctx->devs[k].dev);
+		cudaStreamSynchronize(m->ctx->devs[k].compute);
+		cudaFree(m->dev[k].blob); cudaFree(m->dev[k].dp_src); cudaFree(m->dev[k].hmm_label);
+		cudaFree(m->dev[k].seg_type); cudaFree(m->dev[k].tmat);
+	}
+	delete m;
+}
+
+extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, int max_len, tdg_model** out)
+{
+	if (!ctx || !out) return fail(TDG_EINVAL, "tdg_model_create: NULL argument");
+	*out = nullptr;
+	if (max_len < 1) return fail(TDG_EINVAL, "max_len must be >= 1");
+	auto* m = new tdg_model();
+	m->ctx = ctx;
+	m->max_len = max_len;
+	std::string err;
+	int rc = derive_model(desc, m->hm, err);
+	if (rc != TDG_OK) { delete m; return fail(rc, "%s", err.c_str()); }
+	const HostModel& hm = m->hm;
+	const size_t smem = decode_smem_bytes((int)hm.blob.size());
+	const size_t W = (size_t)max_len + 2;
+	m->slot_bytes_bwd = (size_t)hm.S * W * 4;
+	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 4 +
+	                     (size_t)max_len * hm.H;
+	m->dev.resize(ctx->devs.size());
+	for (size_t k = 0; k < ctx->devs.size(); k++) {
+		DeviceCtx& d = ctx->devs[k];
+		if (smem > d.smem_optin) {
+			tdg_model_destroy(m);
+			return fail(TDG_EINVAL, "architecture too large for shared memory: needs %zu B, device allows %zu B", smem, d.smem_optin);
+		}
+		cudaSetDevice(d.dev);
+		if ((int)smem > d.configured_smem) {
+			// allow the maximum once so later (larger) models need no reconfiguration
+			const int e = kernels_configure((int)d.smem_optin);
+			if (e) { tdg_model_destroy(m); return fail(TDG_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)e)); }
+			d.configured_smem = (int)d.smem_optin;
+		}
+		ModelDev& md = m->dev[k];
+		if ((rc = upload(&md.blob, hm.blob)) || (rc = upload(&md.dp_src, hm.dp_src)) || (rc = upload(&md.hmm_label, hm.label)) ||
+		    (rc = upload(&md.seg_type, hm.seg_type)) || (rc = upload(&md.tmat, hm.tmat))) {
+			tdg_model_destroy(m);
+			return rc;
+		}
+	}
+	*out = m;
+	return TDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batches
+// ------------------------------------------------------------------------------------------
+struct Shard {  // one device's part of a batch
+	int first = 0, n = 0;  // read range (first is a multiple of 32)
+	cudaStream_t copy = nullptr;
+	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
+	int cap = 0;  // reads of device capacity
+	uint32_t* seq = nullptr; int32_t* len = nullptr;
+	float *mapq = nullptr, *bar_prob = nullptr, *f = nullptr, *b = nullptr, *r = nullptr;
+	int32_t *read_type = nullptr, *barcode = nullptr, *fingerprint = nullptr;
+	uint8_t *extracted = nullptr, *labels = nullptr;
+};
+
+struct tdg_batch {
+	tdg_context* ctx = nullptr;
+	int max_reads = 0, max_len = 0, words = 0, label_stride = 0, n = 0;
+	// pinned host staging
+	uint32_t* h_seq = nullptr; int32_t* h_len = nullptr;
+	float *h_mapq = nullptr, *h_bar_prob = nullptr, *h_f = nullptr, *h_b = nullptr, *h_r = nullptr;
+	int32_t *h_read_type = nullptr, *h_barcode = nullptr, *h_fingerprint = nullptr;
+	uint8_t *h_extracted = nullptr, *h_labels = nullptr;
+	std::vector<Shard> shard;
+	int pending_mode = 0; bool pending = false, want_labels = false;
+};
+
+template <class T>
+static int pinned(T** p, size_t n) { CK(cudaHostAlloc((void**)p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocPortable)); return TDG_OK; }
+template <class T>
+static int devalloc(T** p, size_t n) { CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T))); return TDG_OK; }
+
+extern "C" void tdg_batch_destroy(tdg_batch* b)
+{
+	if (!b) return;
+	for (size_t k = 0; k < b->shard.size(); k++) {
+		Shard& s = b->shard[k];
+		cudaSetDevice(b->ctx->devs[k].dev);
+		if (s.copy) cudaStreamSynchronize(s.copy);
+		cudaStreamSynchronize(b->ctx->devs[k].compute);
+		cudaFree(s.seq); cudaFree(s.len); cudaFree(s.mapq); cudaFree(s.bar_prob); cudaFree(s.f); cudaFree(s.b); cudaFree(s.r);
+		cudaFree(s.read_type); cudaFree(s.barcode); cudaFree(s.fingerprint); cudaFree(s.extracted); cudaFree(s.labels);
+		if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+		if (s.k_done) cudaEventDestroy(s.k_done);
+		if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+		if (s.copy) cudaStreamDestroy(s.copy);
+	}
+	cudaFreeHost(b->h_seq); cudaFreeHost(b->h_len); cudaFreeHost(b->h_mapq); cudaFreeHost(b->h_bar_prob); cudaFreeHost(b->h_f);
+	cudaFreeHost(b->h_b); cudaFreeHost(b->h_r); cudaFreeHost(b->h_read_type); cudaFreeHost(b->h_barcode);
+	cudaFreeHost(b->h_fingerprint); cudaFreeHost(b->h_extracted); cudaFreeHost(b->h_labels);
+	delete b;
+}
+
+extern "C" int tdg_batch_create(tdg_context* ctx, int max_reads, int max_len, tdg_batch** out)
+{
+	if (!ctx || !out) return fail(TDG_EINVAL, "tdg_batch_create: NULL argument");
+	*out = nullptr;
+	if (max_reads < 1 || max_len < 1) return fail(TDG_EINVAL, "max_reads and max_len must be >= 1");
+	auto* b = new tdg_batch();
+	b->ctx = ctx;
+	b->max_reads = (max_reads + 31) / 32 * 32;
+	b->max_len = max_len;
+	b->words = (max_len + 1 + 7) / 8;
+	b->label_stride = (max_len + 1 + 7) / 8 * 8;
+	const size_t N = b->max_reads;
+	int rc;
+	if ((rc = pinned(&b->h_seq, N * b->words)) || (rc = pinned(&b->h_len, N)) || (rc = pinned(&b->h_mapq, N)) ||
+	    (rc = pinned(&b->h_bar_prob, N)) || (rc = pinned(&b->h_f, N)) || (rc = pinned(&b->h_b, N)) || (rc = pinned(&b->h_r, N)) ||
+	    (rc = pinned(&b->h_read_type, N)) || (rc = pinned(&b->h_barcode, N)) || (rc = pinned(&b->h_fingerprint, N)) ||
+	    (rc = pinned(&b->h_extracted, N)) || (rc = pinned(&b->h_labels, N * b->label_stride))) {
+		tdg_batch_destroy(b);
+		return rc;
+	}
+	memset(b->h_seq, 0, N * b->words * 4);
+	const int nd = (int)ctx->devs.size();
+	b->shard.resize(nd);
+	const int tiles = (int)(N / 32);
+	const int per = (tiles + nd - 1) / nd * 32;
+	for (int k = 0; k < nd; k++) {
+		Shard& s = b->shard[k];
+		cudaSetDevice(ctx->devs[k].dev);
+		s.cap = per;
+		const size_t P = per;
+		if ((rc = devalloc(&s.seq, P * b->words)) || (rc = devalloc(&s.len, P)) || (rc = devalloc(&s.mapq, P)) ||
+		    (rc = devalloc(&s.bar_prob, P)) || (rc = devalloc(&s.f, P)) || (rc = devalloc(&s.b, P)) || (rc = devalloc(&s.r, P)) ||
+		    (rc = devalloc(&s.read_type, P)) || (rc = devalloc(&s.barcode, P)) || (rc = devalloc(&s.fingerprint, P)) ||
+		    (rc = devalloc(&s.extracted, P)) || (rc = devalloc(&s.labels, P * b->label_stride))) {
+			tdg_batch_destroy(b);
+			return rc;
+		}
+		if (cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming) != cudaSuccess) {
+			tdg_batch_destroy(b);
+			return fail(TDG_ECUDA, "stream/event creation failed");
+		}
+	}
+	*out = b;
+	return TDG_OK;
+}
+
+extern "C" int tdg_batch_clear(tdg_batch* b)
+{
+	if (!b) return fail(TDG_EINVAL, "NULL batch");
+	b->n = 0;
+	return TDG_OK;
+}
+extern "C" int tdg_batch_size(const tdg_batch* b) { return b ? b->n : 0; }
+
+static inline void pack_read(tdg_batch* b, int r, const uint8_t* codes, int len)
+{
+	// tile layout [tile][word][lane]; the code after the last base (the reference's NUL, or the
+	// next base of a windowed read) is packed too: backward() reads it (barcode_hmm.c:3516)
+	uint32_t* base = b->h_seq + ((size_t)(r >> 5) * b->words) * 32 + (r & 31);
+	const int total = len + 1;
+	int pos = 0;
+	for (int w = 0; w < b->words; w++) {
+		uint32_t v = 0;
+		for (int k = 0; k < 8 && pos < total; k++, pos++) v |= (uint32_t)(codes[pos] & 0xF) << (4 * k);
+		base[(size_t)w * 32] = v;
+	}
+	b->h_len[r] = len;
+}
+
+extern "C" int tdg_batch_append_codes(tdg_batch* b, int n, const uint8_t* codes, size_t stride, const int32_t* len)
+{
+	if (!b || !codes || !len) return fail(TDG_EINVAL, "NULL argument");
+	if (b->n + n > b->max_reads) return fail(TDG_EINVAL, "batch overflow: %d + %d > %d", b->n, n, b->max_reads);
+	for (int i = 0; i < n; i++) {
+		if (len[i] < 0 || len[i] > b->max_len) return fail(TDG_EINVAL, "read %d: length %d exceeds batch max_len %d", i, len[i], b->max_len);
+		if ((size_t)len[i] + 1 > stride) return fail(TDG_EINVAL, "read %d: stride %zu too small for length %d + terminator", i, stride, len[i]);
+		pack_read(b, b->n + i, codes + (size_t)i * stride, len[i]);
+	}
+	b->n += n;
+	return TDG_OK;
+}
+
+extern "C" int tdg_batch_append_records(tdg_batch* b, int n, const void* const* records, size_t seq_off, size_t len_off)
+{
+	if (!b || !records) return fail(TDG_EINVAL, "NULL argument");
+	if (b->n + n > b->max_reads) return fail(TDG_EINVAL, "batch overflow: %d + %d > %d", b->n, n, b->max_reads);
+	for (int i = 0; i < n; i++) {
+		const char* rec = (const char*)records[i];
+		const uint8_t* seq = *(const uint8_t* const*)(rec + seq_off);
+		const int len = *(const int*)(rec + len_off);
+		if (len < 0 || len > b->max_len) return fail(TDG_EINVAL, "read %d: length %d exceeds batch max_len %d", i, len, b->max_len);
+		pack_read(b, b->n + i, seq, len);
+	}
+	b->n += n;
+	return TDG_OK;
+}
+
+static void assign_shards(tdg_batch* b)
+{
+	const int nd = (int)b->shard.size();
+	const int tiles = (b->n + 31) / 32;
+	const int per = (tiles + nd - 1) / nd * 32;
+	int first = 0;
+	for (int k = 0; k < nd; k++) {
+		Shard& s = b->shard[k];
+		s.first = std::min(first, b->n);
+		s.n = std::max(0, std::min(per, b->n - s.first));
+		first += per;
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel queueing
+// ------------------------------------------------------------------------------------------
+static void fill_model_args(KArgs& a, const tdg_model* m, int devk, const DeviceCtx& d)
+{
+	const HostModel& hm = m->hm;
+	memset(&a, 0, sizeof a);
+	a.S = hm.S; a.H = hm.H; a.C = hm.C;
+	for (int s = 0; s < hm.S; s++) a.seg[s] = hm.seg[s];
+	a.model_blob = m->dev[devk].blob;
+	a.model_floats = (int)hm.blob.size();
+	a.logsum_tab = d.d_tab;
+	a.r_step = hm.r_step; a.r_end = hm.r_end;
+	for (int k = 0; k < 5; k++) a.bg[k] = hm.bg[k];
+	a.lmax = m->max_len;
+	a.dp_src = m->dev[devk].dp_src;
+	a.hmm_label = m->dev[devk].hmm_label;
+	a.seg_type = m->dev[devk].seg_type;
+	a.tmat = m->dev[devk].tmat;
+	a.dp_structured = hm.dp_structured;
+	a.required_finger_len = hm.required_finger_len;
+}
+
+static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool full)
+{
+	const HostModel& hm = m->hm;
+	const size_t slots = (size_t)d.ctas * kBlock;
+	const size_t W = (size_t)m->max_len + 2;
+	char* p = (char*)d.scratch;
+	auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) / 256 * 256; return q; };
+	a.sb = (float*)take(slots * hm.S * W * 4);
+	if (full) {
+		a.sf = (float*)take(slots * hm.S * W * 4);
+		a.tp = (float*)take(slots * hm.H * 4);
+		a.post = (float*)take(slots * (size_t)m->max_len * hm.H * 4);
+		a.path = (uint8_t*)take(slots * (size_t)m->max_len * hm.H);
+		a.bw = (float2*)take(slots * (size_t)hm.C * m->max_len * 8);
+	}
+}
+
+static size_t scratch_need(const tdg_model* m, const DeviceCtx& d, bool full)
+{
+	const size_t slots = (size_t)d.ctas * kBlock;
+	return slots * (full ? m->slot_bytes_full : m->slot_bytes_bwd) + 8 * 256;
+}
+
+// Queue all waves of one shard on `stream`.  Returns kernel launches queued (<0 on error).
+static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_params* p, tdg_batch* b, int devk,
+                        cudaStream_t stream, float* b_score_override)
+{
+	DeviceCtx& d = ctx->devs[devk];
+	Shard& s = b->shard[devk];
+	if (s.n == 0) return 0;
+	const bool bwd_only = (mode == TDG_MODE_ARCH_COMP);
+	const bool want_labels = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p && p->want_labels);
+	KArgs a;
+	fill_model_args(a, m, devk, d);
+	carve_scratch(a, m, d, !bwd_only);
+	a.words = b->words;
+	a.win_start = 0; a.win_len = -1;
+	if (p && (p->matchstart != -1 || p->matchend != -1)) { a.win_start = p->matchstart; a.win_len = p->matchend - p->matchstart; }
+	a.label_stride = b->label_stride;
+	a.confidence_threshold = p ? p->confidence_threshold : 0.0f;
+	a.minlen = p ? p->minlen : 0;
+	a.dust = (p && mode == TDG_MODE_GET_LABEL) ? p->dust : 0;
+	a.do_extract = (mode == TDG_MODE_GET_LABEL);
+	a.want_labels = want_labels;
+	const int wave = d.ctas * kBlock;
+	int launches = 0;
+	for (int w0 = 0; w0 < s.n; w0 += wave) {
+		const int nw = std::min(wave, s.n - w0);
+		a.n_reads = nw;
+		a.seq = s.seq + (size_t)(w0 / 32) * b->words * 32;
+		a.len = s.len + w0;
+		a.b_score = (b_score_override ? b_score_override : s.b) + w0;
+		a.f_score = s.f + w0; a.r_score = s.r + w0; a.bar_prob = s.bar_prob + w0; a.mapq = s.mapq + w0;
+		a.read_type = s.read_type + w0; a.barcode = s.barcode + w0; a.fingerprint = s.fingerprint + w0;
+		a.extracted = s.extracted + w0;
+		a.labels = s.labels + (size_t)w0 * b->label_stride;
+		const int ctas = (nw + kBlock - 1) / kBlock;
+		int e;
+		if ((e = launch_backward(a, !bwd_only, ctas, stream))) { fail(TDG_ECUDA, "k_backward launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
+		launches++;
+		if (!bwd_only) {
+			if ((e = launch_forward(a, ctas, stream))) { fail(TDG_ECUDA, "k_forward launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
+			launches++;
+			if (want_labels || a.do_extract) {
+				if ((e = launch_label(a, ctas, stream))) { fail(TDG_ECUDA, "k_label launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
+				launches++;
+			}
+		}
+	}
+	return launches;
+}
+
+static int check_compat(tdg_model* m, tdg_batch* b, const tdg_run_params* p)
+{
+	if (!m || !b) return fail(TDG_EINVAL, "NULL model or batch");
+	if (m->ctx != b->ctx) return fail(TDG_EINVAL, "model and batch belong to different contexts");
+	int need = b->max_len;
+	if (p && (p->matchstart != -1 || p->matchend != -1)) {
+		if (p->matchstart < 0 || p->matchend <= p->matchstart) return fail(TDG_EINVAL, "bad -start/-end window %d..%d", p->matchstart, p->matchend);
+		need = p->matchend - p->matchstart;
+		for (int i = 0; i < b->n; i++)
+			if (b->h_len[i] < p->matchend) return fail(TDG_EINVAL, "read %d (length %d) shorter than the -end window %d", i, b->h_len[i], p->matchend);
+	} else {
+		need = 0;
+		for (int i = 0; i < b->n; i++) need = std::max(need, b->h_len[i]);
+	}
+	if (need > m->max_len) return fail(TDG_EINVAL, "read length %d exceeds the model's max_len %d (rebuild the model, cf. barcode_hmm.c:292-310)", need, m->max_len);
+	return TDG_OK;
+}
+
+static int upload_shard(tdg_batch* b, int k, cudaStream_t st)
+{
+	Shard& s = b->shard[k];
+	if (s.n == 0) return TDG_OK;
+	const size_t tiles = (s.n + 31) / 32;
+	CK(cudaMemcpyAsync(s.seq, b->h_seq + (size_t)(s.first / 32) * b->words * 32, tiles * b->words * 32 * 4, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(s.len, b->h_len + s.first, (size_t)s.n * 4, cudaMemcpyHostToDevice, st));
+	return TDG_OK;
+}
+
+static int download_shard(tdg_batch* b, int k, cudaStream_t st, int mode, bool want_labels)
+{
+	Shard& s = b->shard[k];
+	if (s.n == 0) return TDG_OK;
+	const size_t n = s.n, f = s.first;
+	CK(cudaMemcpyAsync(b->h_b + f, s.b, n * 4, cudaMemcpyDeviceToHost, st));
+	if (mode == TDG_MODE_ARCH_COMP) return TDG_OK;
+	CK(cudaMemcpyAsync(b->h_mapq + f, s.mapq, n * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(b->h_bar_prob + f, s.bar_prob, n * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(b->h_f + f, s.f, n * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(b->h_r + f, s.r, n * 4, cudaMemcpyDeviceToHost, st));
+	if (want_labels) CK(cudaMemcpyAsync(b->h_labels + f * b->label_stride, s.labels, n * b->label_stride, cudaMemcpyDeviceToHost, st));
+	if (mode == TDG_MODE_GET_LABEL) {
+		CK(cudaMemcpyAsync(b->h_read_type + f, s.read_type, n * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(b->h_barcode + f, s.barcode, n * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(b->h_fingerprint + f, s.fingerprint, n * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(b->h_extracted + f, s.extracted, n, cudaMemcpyDeviceToHost, st));
+	}
+	return TDG_OK;
+}
+
+static void fill_result(tdg_batch* b, tdg_result* out)
+{
+	if (!out) return;
+	out->n_reads = b->n; out->label_stride = b->label_stride;
+	out->mapq = b->h_mapq; out->bar_prob = b->h_bar_prob; out->f_score = b->h_f; out->b_score = b->h_b; out->r_score = b->h_r;
+	out->read_type = b->h_read_type; out->extracted = b->h_extracted; out->barcode = b->h_barcode;
+	out->fingerprint = b->h_fingerprint; out->labels = b->h_labels;
+}
+
+extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_params* p, tdg_batch* b)
+{
+	if (!ctx) return fail(TDG_EINVAL, "NULL context");
+	if (mode != TDG_MODE_GET_LABEL && mode != TDG_MODE_GET_PROB && mode != TDG_MODE_ARCH_COMP)
+		return fail(TDG_EINVAL, "unsupported mode %d (MODE_TRAIN has no live caller in the reference)", mode);
+	if (mode != TDG_MODE_ARCH_COMP && !p) return fail(TDG_EINVAL, "run params required");
+	int rc = check_compat(m, b, p);
+	if (rc) return rc;
+	if (b->pending) return fail(TDG_EINVAL, "batch already submitted; call tdg_wait first");
+	assign_shards(b);
+	const bool want_labels = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p->want_labels);
+	for (size_t k = 0; k < ctx->devs.size(); k++) {
+		DeviceCtx& d = ctx->devs[k];
+		Shard& s = b->shard[k];
+		if (s.n == 0) continue;
+		CK(cudaSetDevice(d.dev));
+		if ((rc = ensure_scratch(d, scratch_need(m, d, mode != TDG_MODE_ARCH_COMP)))) return rc;
+		if ((rc = upload_shard(b, (int)k, s.copy))) return rc;
+		CK(cudaEventRecord(s.h2d_done, s.copy));
+		CK(cudaStreamWaitEvent(d.compute, s.h2d_done, 0));
+		if (queue_decode(ctx, m, mode, p, b, (int)k, d.compute, nullptr) < 0) return TDG_ECUDA;
+		CK(cudaEventRecord(s.k_done, d.compute));
+		CK(cudaStreamWaitEvent(s.copy, s.k_done, 0));
+		if ((rc = download_shard(b, (int)k, s.copy, mode, want_labels))) return rc;
+		CK(cudaEventRecord(s.d2h_done, s.copy));
+	}
+	b->pending = true; b->pending_mode = mode; b->want_labels = want_labels;
+	return TDG_OK;
+}
+
+extern "C" int tdg_wait(tdg_batch* b, tdg_result* out)
+{
+	if (!b) return fail(TDG_EINVAL, "NULL batch");
+	if (!b->pending) return fail(TDG_EINVAL, "nothing submitted on this batch");
+	for (size_t k = 0; k < b->shard.size(); k++) {
+		if (b->shard[k].n == 0) continue;
+		CK(cudaSetDevice(b->ctx->devs[k].dev));
+		CK(cudaEventSynchronize(b->shard[k].d2h_done));
+	}
+	b->pending = false;
+	fill_result(b, out);
+	return TDG_OK;
+}
+
+extern "C" int tdg_run(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_params* p, tdg_batch* b, tdg_result* out)
+{
+	int rc = tdg_submit(ctx, m, mode, p, b);
+	if (rc) return rc;
+	return tdg_wait(b, out);
+}
+
+// MODE_ARCH_COMP: run_pHMM :1924-1938 + do_arch_comparison :2111-2148 + merge :1994-2017
+extern "C" int tdg_arch_compare(tdg_context* ctx, tdg_model* const* models, int num_arch, tdg_batch* b, int num_threads,
+                                float* b_scores, float* arch_posterior)
+{
+	if (!ctx || !models || !b || !arch_posterior || num_arch < 1) return fail(TDG_EINVAL, "bad argument");
+	if (num_threads < 1) num_threads = 1;
+	const int n = b->n;
+	std::vector<float> all((size_t)num_arch * n);
+	for (int a = 0; a < num_arch; a++) {
+		int rc = tdg_run(ctx, models[a], TDG_MODE_ARCH_COMP, nullptr, b, nullptr);
+		if (rc) return rc;
+		memcpy(all.data() + (size_t)a * n, b->h_b, (size_t)n * 4);
+	}
+	if (b_scores) memcpy(b_scores, all.data(), all.size() * 4);
+	// per-"thread" float sums in read order over the reference's static slices, added in thread order
+	const int interval = (int)((double)n / (double)num_threads);
+	for (int a = 0; a < num_arch; a++) {
+		float total = 0.0f;  // ab->arch_posterior[a] = prob2scaledprob(1.0)
+		for (int t = 0; t < num_threads; t++) {
+			const int s = t * interval, e = (t == num_threads - 1) ? n : t * interval + interval;
+			float part = 0.0f;
+			for (int i = s; i < e; i++) part += all[(size_t)a * n + i];
+			total += part;
+		}
+		arch_posterior[a] = total;
+	}
+	float sum = arch_posterior[0];
+	for (int a = 1; a < num_arch; a++) sum = tdg_logsum_host(sum, arch_posterior[a]);
+	for (int a = 0; a < num_arch; a++) arch_posterior[a] = arch_posterior[a] - sum;
+	return TDG_OK;
+}
+
+// ---- device-resident path ------------------------------------------------------------------
+extern "C" int tdg_batch_upload(tdg_context* ctx, tdg_batch* b)
+{
+	if (!ctx || !b) return fail(TDG_EINVAL, "NULL argument");
+	assign_shards(b);
+	for (size_t k = 0; k < ctx->devs.size(); k++) {
+		if (b->shard[k].n == 0) continue;
+		CK(cudaSetDevice(ctx->devs[k].dev));
+		int rc = upload_shard(b, (int)k, b->shard[k].copy);
+		if (rc) return rc;
+		CK(cudaStreamSynchronize(b->shard[k].copy));
+	}
+	return TDG_OK;
+}
+
+extern "C" int tdg_decode_resident(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_params* p, tdg_batch* b,
+                                   void* cuda_stream, int* n_launches)
+{
+	if (!ctx) return fail(TDG_EINVAL, "NULL context");
+	int rc = check_compat(m, b, p);
+	if (rc) return rc;
+	int total = 0;
+	for (size_t k = 0; k < ctx->devs.size(); k++) {
+		DeviceCtx& d = ctx->devs[k];
+		if (b->shard[k].n == 0) continue;
+		CK(cudaSetDevice(d.dev));
+		if ((rc = ensure_scratch(d, scratch_need(m, d, mode != TDG_MODE_ARCH_COMP)))) return rc;
+		// a caller-provided stream is only meaningful for a single-device context
+		cudaStream_t st = (ctx->devs.size() == 1) ? (cudaStream_t)cuda_stream : d.compute;
+		const int l = queue_decode(ctx, m, mode, p, b, (int)k, st, nullptr);
+		if (l < 0) return TDG_ECUDA;
+		total += l;
+	}
+	if (n_launches) *n_launches = total;
+	return TDG_OK;
+}
+
+extern "C" int tdg_batch_download(tdg_batch* b, tdg_result* out)
+{
+	if (!b) return fail(TDG_EINVAL, "NULL batch");
+	for (size_t k = 0; k < b->shard.size(); k++) {
+		if (b->shard[k].n == 0) continue;
+		CK(cudaSetDevice(b->ctx->devs[k].dev));
+		CK(cudaDeviceSynchronize());
+		int rc = download_shard(b, (int)k, b->shard[k].copy, TDG_MODE_GET_LABEL, true);
+		if (rc) return rc;
+		CK(cudaStreamSynchronize(b->shard[k].copy));
+	}
+	fill_result(b, out);
+	return TDG_OK;
+}
+
+extern "C" double tdg_batch_cells(const tdg_model* m, const tdg_batch* b)
+{
+	if (!m || !b) return 0.0;
+	double cells = 0.0;
+	for (int i = 0; i < b->n; i++) cells += 2.0 * (double)b->h_len[i] * (double)m->hm.C;
+	return cells;
+}

@@ -1,0 +1,724 @@
+// tdg_kernels.cu -- hand-written sm_100a kernels for the TagDust2 per-read HMM decode path.
+//
+// Reference behaviour reproduced (files under the reference's src/):
+//   backward()                         barcode_hmm.c:3439-3640
+//   forward_max_posterior_decoding()   barcode_hmm.c:4128-4525
+//   Q score                            barcode_hmm.c:2316-2338 (do_label_thread), :2216-2234
+//   extract_reads()                    barcode_hmm.c:3172-3313
+//   logsum()                           misc.c:72-78
+//
+// Design: thread-per-read -- the reference's logsum() is not associative and
+// the silent-state chain is strictly ordered, so one thread walks one read in the reference's
+// exact operation order and 75 776 reads are in flight per GPU.  Three kernels per wave:
+//   k_backward : backward pass; Mb/Ib of every (column, position) go to HBM scratch
+//   k_forward  : forward pass + posterior accumulation + total_prob + bar_prob + r_score + Q
+//   k_label    : exp() of the posterior matrix, constrained label DP, traceback, extraction
+// The 16 000-entry logsum table and the compiled architecture live in shared memory.
+// Terms whose transition is log(0) are never evaluated: logsum(x, -inf) == x exactly.
+//
+// Compiled with -fmad=false: the reference binary contains no fused multiply-adds.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <cstdint>
+#include <cstdio>
+#include "tdg_device.h"
+
+namespace tdg {
+
+#define NEG_INF (-CUDART_INF_F)
+constexpr int kDynMaxCols = 64;
+
+// ------------------------------------------------------------------------------------------
+// logsum (misc.c:72-78).  The device table is the host table with entries >= 15700 set to +0:
+// (max-min) >= 15.7f  <=>  (int)((max-min)*1000.0f) >= 15700, so `max + tab[idx]` returns max
+// exactly where the reference returns max, and the clamp maps +inf / NaN differences
+// (min == -inf, or both -inf) to an entry that is 0 as well.  No branch, no select.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float LS(float a, float b, const float* __restrict__ tab)
+{
+	const float mx = fmaxf(a, b);
+	const float mn = fminf(a, b);
+	const float d = mx - mn;
+	const float p = fminf(d * 1000.0f, 15999.0f);
+	return mx + tab[__float2int_rz(p)];
+}
+
+template <int NC, bool STD>
+struct Cols {
+	static constexpr int N = NC > 0 ? NC : kDynMaxCols;
+};
+
+template <bool STD>
+__device__ __forceinline__ bool live_of(int nc, int g, int field, uint32_t mask)
+{
+	if (STD) return std_live(nc, g, field);
+	return (mask >> field) & 1u;
+}
+
+struct Smem {
+	const float* tab;     // 16000 logsum entries
+	const float* colrec;  // C * 12
+	const float* emit;    // C * 10
+};
+
+__device__ __forceinline__ Smem stage_smem(const KArgs& a, float* smem)
+{
+	for (int k = threadIdx.x; k < kLogsumSize; k += blockDim.x) smem[k] = a.logsum_tab[k];
+	float* m = smem + kLogsumSize;
+	for (int k = threadIdx.x; k < a.model_floats; k += blockDim.x) m[k] = a.model_blob[k];
+	__syncthreads();
+	Smem s;
+	s.tab = smem;
+	s.colrec = m;
+	s.emit = m + (size_t)a.C * kColRec;
+	return s;
+}
+
+// packed sequence access: tile layout [tile][word][lane], 8 codes of 4 bits per word.
+struct SeqReader {
+	const uint32_t* base;  // points at word 0 of this lane
+	__device__ __forceinline__ int code(int pos) const
+	{
+		const uint32_t w = base[(size_t)(pos >> 3) * 32];
+		return (w >> ((pos & 7) * 4)) & 0xF;
+	}
+};
+
+__device__ __forceinline__ SeqReader make_reader(const KArgs& a, int read)
+{
+	SeqReader r;
+	r.base = a.seq + ((size_t)(read >> 5) * a.words) * 32 + (read & 31);
+	return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, one segment (all HMMs f, all positions i).  barcode_hmm.c:3496-3607
+// ------------------------------------------------------------------------------------------
+template <int NC, bool STD, bool STORE>
+__device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
+                                            const SeqReader& rd, int off, int len, int lw, bool last_seg,
+                                            float2* __restrict__ bw, float* __restrict__ sb)
+{
+	constexpr int N = Cols<NC, STD>::N;
+	constexpr int UN = NC > 0 ? N : 1;
+	const int nc = NC > 0 ? NC : sg.nc;
+	const int m = nc - 1;
+	const size_t W = (size_t)(a.lmax + 2);
+	float* cs_arr = sb + ((size_t)j * W) * kBlock;
+	const float* ps_arr = sb + ((size_t)(j + 1) * W) * kBlock;
+	const float* tab = sm.tab;
+
+	for (int f = 0; f < sg.nh; ++f) {
+		const int c0 = sg.colbase + f * nc;
+		const float* rec = sm.colrec + (size_t)c0 * kColRec;
+		const float* em = sm.emit + (size_t)c0 * kEmitRec;
+		float M[N], I[N], eMc[N], eIc[N];
+		// state at i = len+1 : all -inf (:3466-3485)
+		const int x_term = rd.code(off + len);  // seqa[len+1] = a[len]  (:3516)
+#pragma unroll UN
+		for (int g = 0; g < N; ++g) {
+			if (g < nc) {
+				M[g] = NEG_INF; I[g] = NEG_INF;
+				eMc[g] = em[g * kEmitRec + x_term];
+				eIc[g] = em[g * kEmitRec + 5 + x_term];
+			}
+		}
+		float ps1 = last_seg ? 0.0f : ps_arr[(size_t)(len + 1) * kBlock];
+		for (int i = lw; i >= 1; --i) {
+			if (i <= len) {
+				const int x0 = rd.code(off + i - 1);  // seqa[i]
+				const float ps0 = last_seg ? NEG_INF : ps_arr[(size_t)i * kBlock];
+				float cs = cs_arr[(size_t)i * kBlock];
+				float eM0[N], eI0[N];
+#pragma unroll UN
+				for (int g = 0; g < N; ++g) {
+					if (g < nc) {
+						eM0[g] = em[g * kEmitRec + x0];
+						eI0[g] = em[g * kEmitRec + 5 + x0];
+					}
+				}
+				// ---- last column (:3518-3541)
+				float oldMp, newMp, D;
+				{
+					const float* r = rec + m * kColRec;
+					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
+					float nM = live_of<STD>(nc, m, F_MSKIP, lv) ? ps1 + r[F_MSKIP] : NEG_INF;
+					float nI = live_of<STD>(nc, m, F_ISKIP, lv) ? ps1 + r[F_ISKIP] : NEG_INF;
+					if (live_of<STD>(nc, m, F_IM, lv)) nI = LS(nI, M[m] + r[F_IM] + eMc[m], tab);
+					if (live_of<STD>(nc, m, F_II, lv)) nI = LS(nI, I[m] + r[F_II] + eIc[m], tab);
+					if (live_of<STD>(nc, m, F_SM, lv)) cs = LS(cs, nM + r[F_SM] + eM0[m], tab);
+					if (live_of<STD>(nc, m, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + eI0[m], tab);
+					oldMp = M[m]; newMp = nM; D = NEG_INF;
+					M[m] = nM; I[m] = nI;
+					if (STORE) bw[((size_t)(c0 + m) * a.lmax + (i - 1)) * kBlock] = make_float2(nM, nI);
+				}
+				// ---- columns m-1 .. 0 (:3545-3589)
+#pragma unroll UN
+				for (int gg = 1; gg < N; ++gg) {
+					const int g = m - gg;
+					if (g >= 0) {
+						const int p = g + 1;
+						const float* r = rec + g * kColRec;
+						const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
+						const float oldMg = M[g];
+						float v;
+						// M_backward[g][i]
+						v = live_of<STD>(nc, g, F_MM, lv) ? oldMp + eMc[p] + r[F_MM] : NEG_INF;
+						if (live_of<STD>(nc, g, F_MSKIP, lv)) v = LS(v, ps1 + r[F_MSKIP], tab);
+						if (live_of<STD>(nc, g, F_MI, lv)) v = LS(v, I[g] + eIc[g] + r[F_MI], tab);
+						if (live_of<STD>(nc, g, F_MD, lv)) v = LS(v, D + r[F_MD], tab);
+						const float nM = v;
+						// I_backward[g][i]
+						v = live_of<STD>(nc, g, F_II, lv) ? I[g] + r[F_II] + eIc[g] : NEG_INF;
+						if (live_of<STD>(nc, g, F_ISKIP, lv)) v = LS(v, ps1 + r[F_ISKIP], tab);
+						if (live_of<STD>(nc, g, F_IM, lv)) v = LS(v, oldMp + r[F_IM] + eMc[p], tab);
+						const float nI = v;
+						// D_backward[g][i]
+						{
+							const bool ldd = live_of<STD>(nc, g, F_DD, lv);
+							const bool ldm = live_of<STD>(nc, g, F_DM, lv);
+							float dv = NEG_INF;
+							if (ldd) dv = D + r[F_DD];
+							if (ldm) {
+								const float t = newMp + eM0[p] + r[F_DM];
+								dv = ldd ? LS(dv, t, tab) : t;
+							}
+							D = dv;
+						}
+						if (live_of<STD>(nc, g, F_SM, lv)) cs = LS(cs, nM + r[F_SM] + eM0[g], tab);
+						if (live_of<STD>(nc, g, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + eI0[g], tab);
+						M[g] = nM; I[g] = nI;
+						oldMp = oldMg; newMp = nM;
+						if (STORE) bw[((size_t)(c0 + g) * a.lmax + (i - 1)) * kBlock] = make_float2(nM, nI);
+					}
+				}
+				if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // once per HMM f (:3604)
+				cs_arr[(size_t)i * kBlock] = cs;
+#pragma unroll UN
+				for (int g = 0; g < N; ++g) {
+					if (g < nc) { eMc[g] = eM0[g]; eIc[g] = eI0[g]; }
+				}
+				ps1 = ps0;
+			}
+		}
+	}
+}
+
+template <bool STORE>
+__global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
+{
+	extern __shared__ float smem_f[];
+	const Smem sm = stage_smem(a, smem_f);
+	const int slot = blockIdx.x * kBlock + threadIdx.x;
+	const int read = slot;
+	const bool valid = read < a.n_reads;
+	int len = 0, off = 0;
+	if (valid) {
+		len = a.len[read];
+		if (a.win_len >= 0) { off = a.win_start; len = a.win_len; }
+	}
+	const int lw = __reduce_max_sync(0xffffffffu, len);
+	const SeqReader rd = make_reader(a, valid ? read : 0);
+	const size_t W = (size_t)(a.lmax + 2);
+	float2* bw = a.bw + (size_t)blockIdx.x * ((size_t)a.C * a.lmax) * kBlock + threadIdx.x;
+	float* sb = a.sb + (size_t)blockIdx.x * ((size_t)a.S * W) * kBlock + threadIdx.x;
+	if (!valid) len = 0;
+
+	// init silent_backward (:3479-3491): -inf, then the len+1 chain of skips
+	for (int j = 0; j < a.S; ++j)
+		for (int i = 0; i <= len + 1; ++i) sb[((size_t)j * W + i) * kBlock] = NEG_INF;
+	{
+		float v = 0.0f + a.seg[a.S - 1].skip;
+		sb[((size_t)(a.S - 1) * W + len + 1) * kBlock] = v;
+		for (int j = a.S - 2; j >= 0; --j) {
+			v = v + a.seg[j].skip;
+			sb[((size_t)j * W + len + 1) * kBlock] = v;
+		}
+	}
+	for (int j = a.S - 1; j >= 0; --j) {
+		const SegInfo sg = a.seg[j];
+		const bool last = (j == a.S - 1);
+		const int kind = sg.kind;  // host-selected code path: 0 generic, 1 STD
+		const int nc = sg.nc;
+#define BWD_CASE(NCV, STDV) bwd_segment<NCV, STDV, STORE>(a, sm, sg, j, rd, off, len, lw, last, bw, sb)
+		if (kind == 1) {
+			switch (nc) {
+				case 3: BWD_CASE(3, true); break;
+				case 4: BWD_CASE(4, true); break;
+				case 5: BWD_CASE(5, true); break;
+				case 6: BWD_CASE(6, true); break;
+				case 7: BWD_CASE(7, true); break;
+				case 8: BWD_CASE(8, true); break;
+				default: BWD_CASE(0, false); break;
+			}
+		} else {
+			switch (nc) {
+				case 1: BWD_CASE(1, false); break;
+				case 2: BWD_CASE(2, false); break;
+				default: BWD_CASE(0, false); break;
+			}
+		}
+#undef BWD_CASE
+	}
+	if (valid) a.b_score[read] = sb[(size_t)1 * kBlock];  // model[0]->silent_backward[1] (:3610)
+}
+
+// ------------------------------------------------------------------------------------------
+// forward + posterior, one segment.  barcode_hmm.c:4199-4345
+// ------------------------------------------------------------------------------------------
+template <int NC, bool STD>
+__device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
+                                            const SeqReader& rd, int off, int len, int lw, float B,
+                                            const float2* __restrict__ bw, float* __restrict__ sf,
+                                            float* __restrict__ post, float* __restrict__ tp)
+{
+	constexpr int N = Cols<NC, STD>::N;
+	constexpr int UN = NC > 0 ? N : 1;
+	const int nc = NC > 0 ? NC : sg.nc;
+	const size_t W = (size_t)(a.lmax + 2);
+	float* cs_arr = sf + ((size_t)j * W) * kBlock;
+	const float* ps_arr = sf + ((size_t)(j - 1) * W) * kBlock;  // only dereferenced when j > 0
+	const float* tab = sm.tab;
+	const bool first_seg = (j == 0);
+	const int skip_live = sg.skip_live;
+
+	for (int f = 0; f < sg.nh; ++f) {
+		const int h = sg.hmmbase + f;
+		const int c0 = sg.colbase + f * nc;
+		const float* rec = sm.colrec + (size_t)c0 * kColRec;
+		const float* em = sm.emit + (size_t)c0 * kEmitRec;
+		float M[N], I[N];
+#pragma unroll UN
+		for (int g = 0; g < N; ++g) {
+			if (g < nc) { M[g] = NEG_INF; I[g] = NEG_INF; }
+		}
+		float TP = NEG_INF;
+		float ps1 = first_seg ? 0.0f : ps_arr[0];  // psilent[0]
+		for (int i = 1; i <= lw; ++i) {
+			if (i <= len) {
+				const int x = rd.code(off + i - 1);  // seqa[i]
+				const float ps0 = first_seg ? NEG_INF : ps_arr[(size_t)i * kBlock];
+				float cs = cs_arr[(size_t)i * kBlock];
+				float P;
+				float oldMp, oldIp, newMp, D;
+				// ---- column 0 (:4218-4266)
+				{
+					const float* r = rec;
+					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
+					const float2 b = bw[((size_t)c0 * a.lmax + (i - 1)) * kBlock];
+					const float eM = em[x], eI = em[5 + x];
+					const bool lsm = live_of<STD>(nc, 0, F_SM, lv);
+					const bool lsi = live_of<STD>(nc, 0, F_SI, lv);
+					const float nM = lsm ? ps1 + r[F_SM] + eM : NEG_INF;
+					const float tM = nM + b.x - B;
+					TP = LS(TP, tM, tab);
+					P = tM;  // logsum(-inf, tM) == tM
+					float v;
+					bool have = false;
+					v = NEG_INF;
+					if (lsi) { v = ps1 + r[F_SI]; have = true; }
+					if (live_of<STD>(nc, 0, F_II, lv)) { const float t = I[0] + r[F_II]; v = have ? LS(v, t, tab) : t; have = true; }
+					if (live_of<STD>(nc, 0, F_MI, lv)) { const float t = M[0] + r[F_MI]; v = have ? LS(v, t, tab) : t; have = true; }
+					const float nI = v + eI;
+					if (lsi) TP = LS(TP, ps1 + r[F_SI] + eI + b.y - B, tab);
+					P = LS(P, nI + b.y - B, tab);
+					if (live_of<STD>(nc, 0, F_MSKIP, lv)) cs = LS(cs, nM + r[F_MSKIP], tab);
+					if (live_of<STD>(nc, 0, F_ISKIP, lv)) cs = LS(cs, nI + r[F_ISKIP], tab);
+					oldMp = M[0]; oldIp = I[0]; newMp = nM; D = NEG_INF;
+					M[0] = nM; I[0] = nI;
+				}
+				// ---- columns 1 .. nc-1 (:4270-4331)
+#pragma unroll UN
+				for (int g = 1; g < N; ++g) {
+					if (g < nc) {
+						const int p = g - 1;
+						const float* r = rec + g * kColRec;
+						const float* rp = rec + p * kColRec;
+						const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
+						const uint32_t lp = STD ? 0u : __float_as_uint(rp[F_LIVE]);
+						const float2 b = bw[((size_t)(c0 + g) * a.lmax + (i - 1)) * kBlock];
+						const float eM = em[g * kEmitRec + x], eI = em[g * kEmitRec + 5 + x];
+						const float oldMg = M[g], oldIg = I[g];
+						float v; bool have;
+						// M_forward[g][i]
+						v = NEG_INF; have = false;
+						if (live_of<STD>(nc, g, F_SM, lv)) { v = ps1 + r[F_SM]; have = true; }
+						if (live_of<STD>(nc, p, F_MM, lp)) { const float t = oldMp + rp[F_MM]; v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, p, F_IM, lp)) { const float t = oldIp + rp[F_IM]; v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, p, F_DM, lp)) { const float t = D + rp[F_DM]; v = have ? LS(v, t, tab) : t; have = true; }
+						const float nM = v + eM;
+						const bool m_reach = STD ? true : have;
+						if (m_reach) P = LS(P, nM + b.x - B, tab);
+						// I_forward[g][i]
+						v = NEG_INF; have = false;
+						if (live_of<STD>(nc, g, F_SI, lv)) { v = ps1 + r[F_SI]; have = true; }
+						if (live_of<STD>(nc, g, F_II, lv)) { const float t = oldIg + r[F_II]; v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, g, F_MI, lv)) { const float t = oldMg + r[F_MI]; v = have ? LS(v, t, tab) : t; have = true; }
+						const float nI = v + eI;
+						if (have) P = LS(P, nI + b.y - B, tab);
+						// D_forward[g][i]
+						{
+							float dv = NEG_INF; bool dh = false;
+							if (live_of<STD>(nc, p, F_MD, lp)) { dv = newMp + rp[F_MD]; dh = true; }
+							if (live_of<STD>(nc, p, F_DD, lp)) { const float t = D + rp[F_DD]; dv = dh ? LS(dv, t, tab) : t; }
+							D = dv;
+						}
+						if (live_of<STD>(nc, g, F_MSKIP, lv)) cs = LS(cs, nM + r[F_MSKIP], tab);
+						if (live_of<STD>(nc, g, F_ISKIP, lv)) cs = LS(cs, nI + r[F_ISKIP], tab);
+						oldMp = oldMg; oldIp = oldIg; newMp = nM;
+						M[g] = nM; I[g] = nI;
+					}
+				}
+				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
+				cs_arr[(size_t)i * kBlock] = cs;
+				post[((size_t)(i - 1) * a.H + h) * kBlock] = P;
+				ps1 = ps0;
+			}
+		}
+		tp[(size_t)h * kBlock] = TP;
+	}
+}
+
+__device__ __forceinline__ float s2p_f(float p)
+{
+	// scaledprob2prob (misc.c:98-105): float argument, double exp, float result
+	if (p == NEG_INF) return 0.0f;
+	return (float)exp((double)p);
+}
+
+__global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
+{
+	extern __shared__ float smem_f[];
+	const Smem sm = stage_smem(a, smem_f);
+	const int slot = blockIdx.x * kBlock + threadIdx.x;
+	const int read = slot;
+	const bool valid = read < a.n_reads;
+	int len = 0, off = 0;
+	if (valid) {
+		len = a.len[read];
+		if (a.win_len >= 0) { off = a.win_start; len = a.win_len; }
+	}
+	const int lw = __reduce_max_sync(0xffffffffu, len);
+	const SeqReader rd = make_reader(a, valid ? read : 0);
+	const size_t W = (size_t)(a.lmax + 2);
+	const float2* bw = a.bw + (size_t)blockIdx.x * ((size_t)a.C * a.lmax) * kBlock + threadIdx.x;
+	float* sf = a.sf + (size_t)blockIdx.x * ((size_t)a.S * W) * kBlock + threadIdx.x;
+	float* post = a.post + (size_t)blockIdx.x * ((size_t)a.lmax * a.H) * kBlock + threadIdx.x;
+	float* tp = a.tp + (size_t)blockIdx.x * ((size_t)a.H) * kBlock + threadIdx.x;
+	const float B = valid ? a.b_score[read] : 0.0f;
+
+	// init silent_forward (:4166-4175)
+	for (int j = 0; j < a.S; ++j)
+		for (int i = 0; i <= len + 1; ++i) sf[((size_t)j * W + i) * kBlock] = NEG_INF;
+	{
+		float v = 0.0f + a.seg[0].skip;
+		sf[0] = v;
+		for (int j = 1; j < a.S; ++j) {
+			v = v + a.seg[j].skip;
+			sf[((size_t)j * W) * kBlock] = v;
+		}
+	}
+	for (int j = 0; j < a.S; ++j) {
+		const SegInfo sg = a.seg[j];
+		const int kind = sg.kind;
+		const int nc = sg.nc;
+#define FWD_CASE(NCV, STDV) fwd_segment<NCV, STDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sf, post, tp)
+		if (kind == 1) {
+			switch (nc) {
+				case 3: FWD_CASE(3, true); break;
+				case 4: FWD_CASE(4, true); break;
+				case 5: FWD_CASE(5, true); break;
+				case 6: FWD_CASE(6, true); break;
+				case 7: FWD_CASE(7, true); break;
+				case 8: FWD_CASE(8, true); break;
+				default: FWD_CASE(0, false); break;
+			}
+		} else {
+			switch (nc) {
+				case 1: FWD_CASE(1, false); break;
+				case 2: FWD_CASE(2, false); break;
+				default: FWD_CASE(0, false); break;
+			}
+		}
+#undef FWD_CASE
+	}
+	if (!valid) return;
+	const float* tab = sm.tab;
+	const float f_score = sf[((size_t)(a.S - 1) * W + len) * kBlock];  // (:4349)
+
+	// total_prob normalisation + bar_prob (:4354-4429); next_silent[0] is never reset.
+	{
+		int h = 0;
+		for (int j = 0; j < a.S; ++j) {
+			const int nh = a.seg[j].nh;
+			if (nh > 1) {
+				float s = NEG_INF;
+				for (int f = 0; f < nh; ++f) s = LS(s, tp[(size_t)(h + f) * kBlock], tab);
+				for (int f = 0; f < nh; ++f) tp[(size_t)(h + f) * kBlock] = tp[(size_t)(h + f) * kBlock] - s;
+			}
+			h += nh;
+		}
+	}
+	float bar_prob;
+	{
+		int h = 0, g = 1;
+		float n0 = NEG_INF, n2 = 0.0f;
+		for (int j = 0; j < a.S; ++j) {
+			const int nh = a.seg[j].nh;
+			if (nh > 1) {
+				g = 0;
+				float n1 = NEG_INF;
+				for (int f = 0; f < nh; ++f) {
+					const float t = tp[(size_t)(h + f) * kBlock];
+					if (t > n0 && f != nh - 1) n0 = t;
+					n1 = LS(n1, t, tab);
+				}
+				n0 = n0 - n1;
+				n2 = n2 + n0;
+			}
+			h += nh;
+		}
+		bar_prob = g ? 0.0f : ((n2 > 0.0f) ? 0.0f : n2);
+	}
+	// random model (:4516-4523)
+	float r = 0.0f;
+	for (int i = 1; i <= len; ++i) {
+		const int c = rd.code(off + i - 1);
+		r = r + a.bg[c < 5 ? c : 4] + a.r_step;
+	}
+	r += a.r_end;
+	// Q (:2320-2338): pbest = logsum(logsum(-inf, f), r); the bar_prob sum is evaluated in double
+	float pbest = LS(NEG_INF, f_score, tab);
+	pbest = LS(pbest, r, tab);
+	const float arg = (float)(((double)bar_prob + (double)f_score) - (double)pbest);
+	pbest = (float)(1.0 - (double)s2p_f(arg));
+	float Q;
+	if (!pbest) Q = 40.0f;
+	else if (pbest == 1.0f) Q = 0.0f;
+	else Q = (float)(-10.0 * log10((double)pbest));
+	a.f_score[read] = f_score;
+	a.r_score[read] = r;
+	a.bar_prob[read] = bar_prob;
+	a.mapq[read] = Q;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_label: exp of posteriors (:4431-4440), constrained label DP (:4447-4472), traceback
+// (:4494-4514), extract_reads (:3172-3313).  Thread-per-read; the posterior matrix is
+// rewritten in place with the DP scores.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float post_exp(float x)
+{
+	// (float)exp((double)x) is exactly 0 below 2^-150 (x < -103.98): skip the double exp there.
+	if (x < -104.0f) return 0.0f;
+	return (float)exp((double)x);
+}
+
+__global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
+{
+	const int slot = blockIdx.x * kDpBlock + threadIdx.x;
+	const int read = slot;
+	if (read >= a.n_reads) return;
+	const int cta = slot / kBlock, t = slot % kBlock;
+	int len = a.len[read], off = 0;
+	const int rlen = len;
+	if (a.win_len >= 0) { off = a.win_start; len = a.win_len; }
+	const int H = a.H;
+	float* post = a.post + (size_t)cta * ((size_t)a.lmax * H) * kBlock + t;
+	uint8_t* path = a.path + (size_t)cta * ((size_t)a.lmax * H) * kBlock + t;
+	uint8_t* labels = a.labels + (size_t)read * a.label_stride;
+
+	if (a.want_labels) {
+		float segmax[kMaxSegments];
+		int segarg[kMaxSegments];
+		// row 0: exp(-inf) = 0 everywhere
+		for (int s = 0; s < a.S; ++s) { segmax[s] = 0.0f; segarg[s] = a.seg[s].hmmbase; }
+		if (a.dp_structured) {
+			for (int i = 1; i <= len; ++i) {
+				float* row = post + ((size_t)(i - 1) * H) * kBlock;
+				const float* prow = post + ((size_t)(i - 2) * H) * kBlock;  // valid when i >= 2
+				uint8_t* prow_path = path + ((size_t)(i - 1) * H) * kBlock;
+				float nsegmax[kMaxSegments];
+				int nsegarg[kMaxSegments];
+				for (int s = 0; s < a.S; ++s) {
+					const int hb = a.seg[s].hmmbase, nh = a.seg[s].nh;
+					float cm = -1.0f; int ca = hb;
+					for (int f = 0; f < nh; ++f) {
+						const int j = hb + f;
+						float best = -1.0f; int arg = -1;
+						for (int k = 0; k < kMaxSources; ++k) {
+							const int src = a.dp_src[j * kMaxSources + k];
+							if (src == INT32_MIN) break;
+							float v; int av;
+							if (src < 0) { v = segmax[-src - 1]; av = segarg[-src - 1]; }
+							else { v = (i >= 2) ? prow[(size_t)src * kBlock] : 0.0f; av = src; }
+							if (v > best) { best = v; arg = av; }
+						}
+						const float self = (i >= 2) ? prow[(size_t)j * kBlock] : 0.0f;
+						float mx; int mv;
+						if (self >= best) { mx = self; mv = j; } else { mx = best; mv = arg; }
+						const float nd = post_exp(row[(size_t)j * kBlock]) + mx;
+						row[(size_t)j * kBlock] = nd;
+						prow_path[(size_t)j * kBlock] = (uint8_t)mv;
+						if (nd > cm) { cm = nd; ca = j; }
+					}
+					nsegmax[s] = cm; nsegarg[s] = ca;
+				}
+				for (int s = 0; s < a.S; ++s) { segmax[s] = nsegmax[s]; segarg[s] = nsegarg[s]; }
+			}
+		} else {
+			// generic O(L*H^2) form, verbatim tie rules (:4453-4464)
+			for (int i = 1; i <= len; ++i) {
+				float* row = post + ((size_t)(i - 1) * H) * kBlock;
+				const float* prow = post + ((size_t)(i - 2) * H) * kBlock;
+				uint8_t* prow_path = path + ((size_t)(i - 1) * H) * kBlock;
+				for (int j = 0; j < H; ++j) {
+					float mx = -1.0f; int mv = -1;
+					for (int c = 0; c <= j; ++c) {
+						const float pv = (i >= 2) ? prow[(size_t)c * kBlock] : 0.0f;
+						const float tmp = pv * (float)a.tmat[c * H + j];
+						if (tmp > mx) { mv = c; mx = tmp; }
+						if (tmp == mx && c == j) { mv = c; mx = tmp; }
+					}
+					row[(size_t)j * kBlock] = post_exp(row[(size_t)j * kBlock]) + mx;
+					prow_path[(size_t)j * kBlock] = (uint8_t)mv;
+				}
+			}
+		}
+		// final argmax, first max wins (:4494-4501)
+		int move = -1;
+		{
+			float mx = -1.0f;
+			for (int j = 0; j < H; ++j) {
+				const float v = (len >= 1) ? post[((size_t)(len - 1) * H + j) * kBlock] : 0.0f;
+				if (v > mx) { mx = v; move = j; }
+			}
+		}
+		for (int i = 0; i <= rlen; ++i) labels[i] = 0;
+		if (move < 0) move = 0;
+		labels[len] = (uint8_t)move;
+		for (int i = len; i > 0; --i) {
+			move = path[((size_t)(i - 1) * H + move) * kBlock];
+			labels[i - 1] = (uint8_t)move;
+		}
+	}
+	if (!a.do_extract) return;
+	// ---- extract_reads (:3172-3313); make_extracted_read's rewrite is done on the host
+	const SeqReader rd = make_reader(a, read);
+	int key = 0, bar = -1, mem = -1, fingerlen = 0, s_pos = 0, hmm_has_barcode = 0, too_short = 0, in_read = 0;
+	int read_type, barcode = -1, fingerprint = -1;
+	const float mapq = a.mapq[read];
+	if (a.confidence_threshold <= mapq) {
+		for (int j = 0; j < len; ++j) {
+			const int c1 = a.hmm_label[labels[j + 1]];
+			const int c2 = c1 & 0xFFFF;
+			const int c3 = (c1 >> 16) & 0x7FFF;
+			const uint8_t ty = a.seg_type[c2];
+			if (ty == 'F') { fingerlen++; key = (key << 2) | (rd.code(j + off) & 0x3); }
+			if (ty == 'B') {
+				hmm_has_barcode = 1; bar = c3;
+				if (bar == a.seg[c2].nh - 1) hmm_has_barcode = -1;
+				mem = c2;
+			}
+			if (ty == 'R') { s_pos++; in_read = 1; }
+			else {
+				if (in_read && s_pos < a.minlen) { too_short = 1; break; }
+				in_read = 0; s_pos = 0;
+			}
+		}
+		if (in_read && s_pos < a.minlen) too_short = 1;
+		const int rfl = a.required_finger_len;
+		const int fp = (key << 8) | (rfl <= 255 ? rfl : 255);
+		if (!too_short) {
+			if (hmm_has_barcode == -1) read_type = 3;
+			else if (hmm_has_barcode && rfl) {
+				if (fingerlen == rfl && bar != -1) { barcode = (mem << 16) | bar; fingerprint = fp; read_type = 0; }
+				else read_type = 3;
+			} else if (hmm_has_barcode) {
+				if (bar != -1) { barcode = (mem << 16) | bar; read_type = 0; }
+				else read_type = 3;
+			} else if (rfl) {
+				if (fingerlen == rfl) { fingerprint = fp; read_type = 0; }
+				else read_type = 3;
+			} else read_type = 0;
+		} else read_type = 2;
+	} else read_type = 1;
+	const bool extracted = (read_type == 0);
+	// ---- dust_sequences (:2407-2467) on the sequence as make_extracted_read (:3325-3356)
+	// leaves it: R-labelled residues keep their base, everything else is the spacer 65.
+	if (a.dust) {
+		auto e = [&](int j) -> int {
+			if (j >= rlen) return 0;  // NUL terminator
+			if (extracted) {
+				const int c2 = a.hmm_label[labels[j + 1]] & 0xFFFF;
+				if (a.seg_type[c2] != 'R') return 65;
+			}
+			return rd.code(j);
+		};
+		uint8_t cnt[64];
+		for (int j = 0; j < 64; ++j) cnt[j] = 0;
+		int c = 0;
+		while (e(c) == 65) c++;
+		unsigned key = ((e(c) & 0x3) << 2) | (e(c + 1) & 0x3);
+		int dl = rlen; if (dl > 64) dl = 64;
+		c += 2;
+		for (int j = c; j < dl; ++j) {
+			const int v = e(j);
+			if (v == 65) break;
+			key = (key << 2) | (v & 0x3);
+			cnt[key & 0x3F]++;
+			c++;
+		}
+		int si = 0;
+		for (int j = 0; j < 64; ++j) si += (int)cnt[j] * ((int)cnt[j] - 1) / 2;
+		double s = (double)si;
+		s = s / (double)(c - 3) * 10.0;
+		if (s > (double)a.dust) read_type = 6;
+	}
+	a.extracted[read] = extracted ? 1 : 0;
+	a.read_type[read] = read_type;
+	a.barcode[read] = barcode;
+	a.fingerprint[read] = fingerprint;
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+size_t decode_smem_bytes(int model_floats) { return (size_t)(kLogsumSize + model_floats) * sizeof(float); }
+
+int kernels_configure(int smem_bytes)
+{
+	cudaError_t e;
+	e = cudaFuncSetAttribute(k_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(k_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+	if (e != cudaSuccess) return (int)e;
+	return 0;
+}
+
+int launch_backward(const KArgs& a, bool store, int ctas, void* stream)
+{
+	const size_t smem = decode_smem_bytes(a.model_floats);
+	if (store) k_backward<true><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	else k_backward<false><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	return (int)cudaGetLastError();
+}
+
+int launch_forward(const KArgs& a, int ctas, void* stream)
+{
+	const size_t smem = decode_smem_bytes(a.model_floats);
+	k_forward<<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	return (int)cudaGetLastError();
+}
+
+int launch_label(const KArgs& a, int ctas_decode, void* stream)
+{
+	const int threads = ctas_decode * kBlock;
+	const int ctas = (threads + kDpBlock - 1) / kDpBlock;
+	k_label<<<ctas, kDpBlock, 0, (cudaStream_t)stream>>>(a);
+	return (int)cudaGetLastError();
+}
+
+}  // namespace tdg
