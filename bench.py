@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the TagDust2 per-read HMM decode path on B200.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun)
+    python bench.py --impl reference ...                   (the reference's CPU run_pHMM)
+
+Workload (BASELINE.json configs[1], "cfg2"): synthetic single-end 150 nt reads, architecture
+`-1 B:<48 six-nt barcodes of EDITTAG_6nt_ed_3> -2 R:N`, 1 % substitution errors in the
+barcode, 5 % uniform-random contaminant reads; MODE_GET_LABEL (backward + forward/posterior
++ label DP + Q + extraction + dust).  A step = one pass of the hot path over one batch.
+
+Prints ONE JSON line on rank 0 (contract in the task statement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tagdust_b200 import synth  # noqa: E402
+
+READ_LEN = 150
+N_BARCODES = 48
+TAGS = os.path.join(ROOT, "tests", "golden", "edittag_6nt_ed3.txt")
+THRESHOLD = 1.5          # a fixed -Q so that every step does the same work (no calibration phase)
+OPS_PER_COLPOS_BWD = 8 * 9 + 18   # 8 logsum (9 FP32-pipe ops each) + 18 adds per column-position
+OPS_PER_COLPOS_FWD = 10 * 9 + 17  # forward/posterior: 10 logsum + 17 adds
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def architecture():
+    tags = synth.load_tags(TAGS, N_BARCODES)
+    return ["B:" + ",".join(tags), "R:N"], tags
+
+
+def background():
+    """ssi->background for uniform A/C/G/T with the +1 pseudocounts of io.c:79-81 on ~1M reads."""
+    counts = np.array([37.5e6 + 1, 37.5e6 + 1, 37.5e6 + 1, 37.5e6 + 1, 1.0])
+    s = counts.sum()
+    return np.array([float(np.float32(np.log(float(np.float32(c / s))))) for c in counts])
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference's run_pHMM on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_rate(n_reads, threads, seed, steps=1, warmup=0):
+    """Times run_pHMM(MODE_GET_LABEL) of oracle/_ref/libtagdust_ref.so (reference compiled from
+    its own sources) on `n_reads` reads of the bench workload with `threads` pthreads.
+    Falls back to the plain-C port (oracle/liboracle.so) when _ref is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refharness
+    segs, tags = architecture()
+    codes, lens, _ = synth.make_reads_fast(n_reads, READ_LEN, tags, error_rate=0.01, random_frac=0.05, seed=seed)
+    times = []
+    if refharness.have_ref():
+        kind = "reference"
+        R = refharness.RefHarness()
+        p = R.param_new(segs, threshold=THRESHOLD, minlen=16, dust=100, threads=threads)
+        mb = R.model_new(p, background=background(), average_length=float(READ_LEN), max_seq_len=READ_LEN)
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            R.run_phmm(mb, p, 1, codes, lens)
+            times.append(time.perf_counter() - t0)
+    else:
+        kind = "port"
+        refharness.build_oracle()
+        from tagdust_b200.api import compile_architecture
+        desc = compile_architecture(segs, background(), float(READ_LEN), READ_LEN)
+        O = refharness.Oracle()
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.run(desc, 1, codes, lens, threshold=THRESHOLD, minlen=16, dust=100, threads=threads)
+            times.append(time.perf_counter() - t0)
+    times = times[warmup:]
+    return kind, n_reads, times
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    n = max(threads * 250, 2000)
+    kind, n, times = cpu_reference_rate(n, threads, seed=1234, steps=args.steps, warmup=args.warmup)
+    total = sum(times)
+    value = n * len(times) / total
+    segs, _ = architecture()
+    C = 48 * 6 + 6 + 1
+    line = {
+        "impl": "reference", "metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 150 nt single-end, -1 B:<48 x 6 nt EDITTAG_6nt_ed_3> -2 R:N, 1% error, 5% random",
+                   "mode": "MODE_GET_LABEL", "threshold": THRESHOLD},
+        "gcups": value * 2 * READ_LEN * C / 1e9,
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind,
+                         "sample": f"{n} reads per step, run_pHMM(MODE_GET_LABEL) with {threads} pthreads"},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from tagdust_b200.api import MODE_GET_LABEL, Context, compile_architecture
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    segs, tags = architecture()
+    desc = compile_architecture(segs, background(), float(READ_LEN), READ_LEN)
+    ctx = Context(device_ids=[local])
+    model = ctx.model(desc, READ_LEN)
+    n_reads = args.reads
+    t0 = time.perf_counter()
+    codes, lens, truth = synth.make_reads_fast(n_reads, READ_LEN, tags, error_rate=0.01, random_frac=0.05, seed=100 + rank)
+    log(f"[rank {rank}] generated {n_reads} reads in {time.perf_counter() - t0:.1f}s")
+    batches = [ctx.batch(n_reads, READ_LEN) for _ in range(2)]
+    kw = dict(threshold=THRESHOLD, minlen=16, dust=100)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- (1) kernel-only: inputs resident in HBM, CUDA events on the launching stream
+    batches[0].append(codes, lens)
+    ctx.upload(batches[0])
+    stream = torch.cuda.current_stream().cuda_stream
+    launches_per_step = 0
+    for _ in range(args.warmup):
+        launches_per_step = ctx.decode_resident(model, batches[0], MODE_GET_LABEL, stream=stream, **kw)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        ctx.decode_resident(model, batches[0], MODE_GET_LABEL, stream=stream, **kw)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = ctx.profile_read(0)
+    ctx.profile_enable(False)
+    clocks = sampler.finish()
+    res = ctx.download(batches[0])
+    assigned_ok = int(((res["barcode"] & 0xFFFF) == truth)[truth >= 0].sum())
+    n_model = int((truth >= 0).sum())
+
+    # ---- (2) end to end through the C ABI with HOST buffers: pack -> H2D -> kernels -> D2H,
+    #          double buffered (pack of step k+1 overlaps the GPU work of step k)
+    for b in batches:
+        b.clear()
+    h2d = n_reads // 32 * 32 * ((READ_LEN + 8) // 8) * 4 + n_reads * 4
+    d2h = n_reads * (5 * 4 + 3 * 4 + 1 + ((READ_LEN + 8) // 8 * 8))
+
+    def e2e_pass(steps):
+        pending = None
+        for s in range(steps):
+            b = batches[s % 2]
+            b.clear()
+            b.append(codes, lens)                      # host pack into pinned 4-bit tiles
+            ctx.submit(model, b, MODE_GET_LABEL, **kw)  # async H2D + kernels + D2H
+            if pending is not None:
+                ctx.wait(pending, copy=False)
+            pending = b
+        ctx.wait(pending, copy=False)
+
+    e2e_pass(min(args.warmup, 2))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pass(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks (max time), rank 0 prints
+    t = torch.tensor([ms_total, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    total_reads = n_reads * world
+    value = total_reads * args.steps / (ms_total / 1000.0)
+    e2e_value = total_reads * args.steps / (e2e_ms / 1000.0)
+    C = desc.total_columns
+    cells_per_read = 2 * READ_LEN * C
+
+    pk, pk_src = peaks()
+    fp32_peak = 148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12   # T lane-ops/s
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    ops_colpos = {"k_backward": OPS_PER_COLPOS_BWD, "k_forward": OPS_PER_COLPOS_FWD, "k_label": 0}
+    dom_ops = n_reads * args.steps * READ_LEN * C * ops_colpos[dom]
+    dom_s = prof[dom]["ms"] / 1000.0
+    achieved = dom_ops / dom_s / 1e12 if dom_s > 0 else 0.0
+    # algorithmic HBM bytes of the backward->forward hand-off: Mb,Ib of every (column, position), written once, read once
+    hbm_bytes = n_reads * args.steps * READ_LEN * C * 8 * 2
+    line = {
+        "metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 150 nt single-end, -1 B:<48 x 6 nt EDITTAG_6nt_ed_3> -2 R:N, 1% error, 5% random",
+                   "mode": "MODE_GET_LABEL", "threshold": THRESHOLD, "reads_per_step_per_gpu": n_reads,
+                   "cells_per_read": cells_per_read,
+                   "l2": "per-step scratch working set (~30 GB) and packed input both exceed the 126 MB L2"},
+        "gcups": value * cells_per_read / 1e9,
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                "gcups": e2e_value * cells_per_read / 1e9,
+                "what": "tdg_batch_append_codes (host pack) + tdg_submit + tdg_wait, double buffered, host arrays in and out"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32", "kernel": dom, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak, "traffic": None,
+                     "ops_per_column_position": ops_colpos[dom],
+                     "peak_source": f"148 SM x 128 FP32 lanes x sm_max_mhz, {pk_src}",
+                     "note": "algorithmic FP32-pipe ops (SURVEY 8d); T lane-ops/s reported in the TFLOP/s unit"},
+        "roofline_whole_path": {"achieved": value / world * READ_LEN * C * (OPS_PER_COLPOS_BWD + OPS_PER_COLPOS_FWD) / 1e12,
+                                "peak": fp32_peak, "unit": "TFLOP/s"},
+        "hbm": {"achieved_gbs": hbm_bytes / ((prof["k_backward"]["ms"] + prof["k_forward"]["ms"]) / 1000.0) / 1e9,
+                "peak_gbs": pk.get("hbm_gbs"), "what": "Mb/Ib scratch write+read over k_backward+k_forward time"},
+        "kernels_ms": prof,
+        "check": {"reads_with_true_barcode_assigned": assigned_ok, "model_reads": n_model,
+                  "read_type_counts": np.bincount(res["read_type"], minlength=7).tolist()},
+    }
+    line["roofline_whole_path"]["frac"] = line["roofline_whole_path"]["achieved"] / fp32_peak
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        n_cpu = max(threads * 500, 4000)
+        kind, n_cpu, times = cpu_reference_rate(n_cpu, threads, seed=1234)
+        cpu_value = n_cpu / times[0]
+        line["cpu_baseline"] = {"value": cpu_value, "unit": "reads/s", "cores": threads, "kind": kind,
+                                "sample": f"{n_cpu} reads of the same workload, run_pHMM(MODE_GET_LABEL), {threads} pthreads, {times[0]:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for b in batches:
+        b.close()
+    model.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=32 * 148 * 512, help="reads per step per GPU (default 32 waves)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

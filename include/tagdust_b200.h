@@ -192,6 +192,11 @@ int  tdg_decode_resident(tdg_context* ctx, tdg_model* m, int mode, const tdg_run
                          tdg_batch* b, void* cuda_stream, int* n_launches);
 int  tdg_batch_download(tdg_batch* b, tdg_result* out);
 
+/* Per-kernel device timing (CUDA events around every launch on the launching stream).
+ * kinds: 0 k_backward, 1 k_forward, 2 k_label.  Read after synchronising. */
+int  tdg_profile_enable(tdg_context* ctx, int on);
+int  tdg_profile_read(tdg_context* ctx, int device_index, float ms[3], int launches[3]);
+
 /* work accounting for the roofline: profile-column cells (2*L*C per read) */
 double tdg_batch_cells(const tdg_model* m, const tdg_batch* b);
 

@@ -187,6 +187,16 @@ class Context:
         _check(self.lib, self.lib.tdg_batch_download(batch.h, C.byref(res)))
         return _result_to_numpy(res, mode, True)
 
+    def profile_enable(self, on=True):
+        _check(self.lib, self.lib.tdg_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, device_index=0):
+        ms = (C.c_float * 3)()
+        nl = (C.c_int * 3)()
+        _check(self.lib, self.lib.tdg_profile_read(self.h, device_index, ms, nl))
+        names = ("k_backward", "k_forward", "k_label")
+        return {names[k]: {"ms": float(ms[k]), "launches": int(nl[k])} for k in range(3)}
+
     def cells(self, model, batch):
         return self.lib.tdg_batch_cells(model.h, batch.h)
 

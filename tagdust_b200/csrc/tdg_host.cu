@@ -85,6 +85,9 @@ struct DeviceCtx {
 	size_t scratch_bytes = 0;
 	size_t smem_optin = 0;
 	int configured_smem = 0;
+	// optional per-kernel timing (tdg_profile_*): event pairs recorded around every launch
+	bool profile = false;
+	std::vector<cudaEvent_t> ev[3];  // [kernel kind] start/stop pairs
 };
 
 struct tdg_context {
@@ -140,9 +143,52 @@ extern "C" void tdg_shutdown(tdg_context* ctx)
 		cudaStreamSynchronize(d.compute);
 		if (d.scratch) cudaFree(d.scratch);
 		if (d.d_tab) cudaFree(d.d_tab);
+		for (int k = 0; k < 3; k++) for (auto e : d.ev[k]) cudaEventDestroy(e);
 		cudaStreamDestroy(d.compute);
 	}
 	delete ctx;
+}
+
+static void prof_mark(DeviceCtx& d, int kind, cudaStream_t st)
+{
+	if (!d.profile) return;
+	cudaEvent_t e;
+	if (cudaEventCreate(&e) != cudaSuccess) return;
+	cudaEventRecord(e, st);
+	d.ev[kind].push_back(e);
+}
+
+extern "C" int tdg_profile_enable(tdg_context* ctx, int on)
+{
+	if (!ctx) return fail(TDG_EINVAL, "NULL context");
+	for (auto& d : ctx->devs) {
+		cudaSetDevice(d.dev);
+		for (int k = 0; k < 3; k++) {
+			for (auto e : d.ev[k]) cudaEventDestroy(e);
+			d.ev[k].clear();
+		}
+		d.profile = on != 0;
+	}
+	return TDG_OK;
+}
+
+// Sums the device time of every k_backward / k_forward / k_label launch recorded since
+// tdg_profile_enable(ctx, 1) on device `devk`; the caller must have synchronised the stream.
+extern "C" int tdg_profile_read(tdg_context* ctx, int devk, float ms[3], int launches[3])
+{
+	if (!ctx || devk < 0 || devk >= (int)ctx->devs.size()) return fail(TDG_EINVAL, "bad device index");
+	DeviceCtx& d = ctx->devs[devk];
+	CK(cudaSetDevice(d.dev));
+	for (int k = 0; k < 3; k++) {
+		ms[k] = 0.0f; launches[k] = (int)d.ev[k].size() / 2;
+		for (size_t i = 0; i + 1 < d.ev[k].size(); i += 2) {
+			float t = 0.0f;
+			CK(cudaEventSynchronize(d.ev[k][i + 1]));
+			CK(cudaEventElapsedTime(&t, d.ev[k][i], d.ev[k][i + 1]));
+			ms[k] += t;
+		}
+	}
+	return TDG_OK;
 }
 
 static int ensure_scratch(DeviceCtx& d, size_t bytes)
@@ -614,13 +660,19 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 		a.labels = s.labels + (size_t)w0 * b->label_stride;
 		const int ctas = (nw + kBlock - 1) / kBlock;
 		int e;
+		prof_mark(d, 0, stream);
 		if ((e = launch_backward(a, !bwd_only, ctas, stream))) { fail(TDG_ECUDA, "k_backward launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
+		prof_mark(d, 0, stream);
 		launches++;
 		if (!bwd_only) {
+			prof_mark(d, 1, stream);
 			if ((e = launch_forward(a, ctas, stream))) { fail(TDG_ECUDA, "k_forward launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
+			prof_mark(d, 1, stream);
 			launches++;
 			if (want_labels || a.do_extract) {
+				prof_mark(d, 2, stream);
 				if ((e = launch_label(a, ctas, stream))) { fail(TDG_ECUDA, "k_label launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
+				prof_mark(d, 2, stream);
 				launches++;
 			}
 		}
