@@ -27,20 +27,34 @@ namespace tdg {
 
 #define NEG_INF (-CUDART_INF_F)
 constexpr int kDynMaxCols = 64;
+constexpr int TDG_MAX_HMMS_DEV = 255;
 
 // ------------------------------------------------------------------------------------------
 // logsum (misc.c:72-78).  The device table is the host table with entries >= 15700 set to +0:
 // (max-min) >= 15.7f  <=>  (int)((max-min)*1000.0f) >= 15700, so `max + tab[idx]` returns max
 // exactly where the reference returns max, and the clamp maps +inf / NaN differences
 // (min == -inf, or both -inf) to an entry that is 0 as well.  No branch, no select.
+// The truncation (int)x is done on the FP32 pipe: x + 2^23 rounded toward zero has floor(x)
+// in its mantissa (0 <= x < 2^23), so its bit pattern << 2 plus a pre-offset shared-memory
+// base is the byte address of tab[(int)x]; no F2I (XU pipe) on the hot path.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float LS(float a, float b, const float* __restrict__ tab)
+typedef uint32_t TabAddr;  // shared-memory byte address of the table minus (0x4B000000 << 2)
+
+__device__ __forceinline__ TabAddr make_tab_addr(const float* tab)
+{
+	return (uint32_t)__cvta_generic_to_shared(tab) - (0x4B000000u << 2);
+}
+
+__device__ __forceinline__ float LS(float a, float b, TabAddr tab)
 {
 	const float mx = fmaxf(a, b);
 	const float mn = fminf(a, b);
 	const float d = mx - mn;
 	const float p = fminf(d * 1000.0f, 15999.0f);
-	return mx + tab[__float2int_rz(p)];
+	const uint32_t bits = __float_as_uint(__fadd_rz(p, 8388608.0f));
+	float t;
+	asm("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(tab + (bits << 2)));
+	return mx + t;
 }
 
 template <int NC, bool STD>
@@ -56,7 +70,7 @@ __device__ __forceinline__ bool live_of(int nc, int g, int field, uint32_t mask)
 }
 
 struct Smem {
-	const float* tab;     // 16000 logsum entries
+	TabAddr tab;          // pre-offset shared address of the 16000 logsum entries
 	const float* colrec;  // C * 12
 	const float* emit;    // C * 10
 };
@@ -68,7 +82,7 @@ __device__ __forceinline__ Smem stage_smem(const KArgs& a, float* smem)
 	for (int k = threadIdx.x; k < a.model_floats; k += blockDim.x) m[k] = a.model_blob[k];
 	__syncthreads();
 	Smem s;
-	s.tab = smem;
+	s.tab = make_tab_addr(smem);
 	s.colrec = m;
 	s.emit = m + (size_t)a.C * kColRec;
 	return s;
@@ -79,7 +93,7 @@ struct SeqReader {
 	const uint32_t* base;  // points at word 0 of this lane
 	__device__ __forceinline__ int code(int pos) const
 	{
-		const uint32_t w = base[(size_t)(pos >> 3) * 32];
+		const uint32_t w = __ldg(base + (size_t)(pos >> 3) * 32);
 		return (w >> ((pos & 7) * 4)) & 0xF;
 	}
 };
@@ -91,12 +105,62 @@ __device__ __forceinline__ SeqReader make_reader(const KArgs& a, int read)
 	return r;
 }
 
+// Register-resident cursors over the packed codes: the current 8-code word and the next one
+// are kept in registers, so the per-position code is a shift+mask and the (coalesced, 128 B
+// per warp) word load is issued 8 positions before its first use.
+struct SeqDown {  // positions pos, pos-1, ...
+	const uint32_t* base; uint32_t wcur, wnext; int pos;
+	__device__ __forceinline__ void init(const SeqReader& rd, int p0)
+	{
+		base = rd.base; pos = p0; wcur = 0; wnext = 0;
+		if (p0 >= 0) {
+			const int wi = p0 >> 3;
+			wcur = __ldg(base + (size_t)wi * 32);
+			if (wi > 0) wnext = __ldg(base + (size_t)(wi - 1) * 32);
+		}
+	}
+	__device__ __forceinline__ int get()
+	{
+		const int x = (wcur >> ((pos & 7) * 4)) & 0xF;
+		if ((pos & 7) == 0) {
+			wcur = wnext;
+			const int wi = (pos >> 3) - 2;
+			if (wi >= 0) wnext = __ldg(base + (size_t)wi * 32);
+		}
+		pos--;
+		return x;
+	}
+};
+struct SeqUp {  // positions pos, pos+1, ...
+	const uint32_t* base; uint32_t wcur, wnext; int pos, words;
+	__device__ __forceinline__ void init(const SeqReader& rd, int p0, int nwords)
+	{
+		base = rd.base; pos = p0; words = nwords;
+		const int wi = p0 >> 3;
+		wcur = __ldg(base + (size_t)wi * 32);
+		wnext = (wi + 1 < words) ? __ldg(base + (size_t)(wi + 1) * 32) : 0u;
+	}
+	__device__ __forceinline__ int get()
+	{
+		const int x = (wcur >> ((pos & 7) * 4)) & 0xF;
+		if ((pos & 7) == 7) {
+			wcur = wnext;
+			const int wi = (pos >> 3) + 2;
+			if (wi < words) wnext = __ldg(base + (size_t)wi * 32);
+		}
+		pos++;
+		return x;
+	}
+};
+
 // ------------------------------------------------------------------------------------------
 // backward, one segment (all HMMs f, all positions i).  barcode_hmm.c:3496-3607
+// The silent-state values of the next iteration (cs_arr[i-1], ps_arr[i-1]) are loaded one
+// position ahead: they come from L2/HBM and would otherwise stall the ordered chain.
 // ------------------------------------------------------------------------------------------
 template <int NC, bool STD, bool STORE>
 __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
-                                            const SeqReader& rd, int off, int len, int lw, bool last_seg,
+                                            const SeqReader& rd, int off, int len, int lw, int x_term, bool last_seg,
                                             float2* __restrict__ bw, float* __restrict__ sb)
 {
 	constexpr int N = Cols<NC, STD>::N;
@@ -106,15 +170,14 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 	const size_t W = (size_t)(a.lmax + 2);
 	float* cs_arr = sb + ((size_t)j * W) * kBlock;
 	const float* ps_arr = sb + ((size_t)(j + 1) * W) * kBlock;
-	const float* tab = sm.tab;
+	const TabAddr tab = sm.tab;
 
 	for (int f = 0; f < sg.nh; ++f) {
 		const int c0 = sg.colbase + f * nc;
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
 		const float* em = sm.emit + (size_t)c0 * kEmitRec;
 		float M[N], I[N], eMc[N], eIc[N];
-		// state at i = len+1 : all -inf (:3466-3485)
-		const int x_term = rd.code(off + len);  // seqa[len+1] = a[len]  (:3516)
+		// state at i = len+1 : all -inf (:3466-3485); emissions of seqa[len+1] = a[len] (:3516)
 #pragma unroll UN
 		for (int g = 0; g < N; ++g) {
 			if (g < nc) {
@@ -124,11 +187,17 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 			}
 		}
 		float ps1 = last_seg ? 0.0f : ps_arr[(size_t)(len + 1) * kBlock];
+		SeqDown sd;
+		sd.init(rd, off + lw - 1);
+		float cs_n = cs_arr[(size_t)lw * kBlock];
+		float ps_n = last_seg ? NEG_INF : ps_arr[(size_t)lw * kBlock];
 		for (int i = lw; i >= 1; --i) {
+			const int x0 = sd.get();  // seqa[i]
+			float cs = cs_n;
+			const float ps0 = ps_n;
+			cs_n = cs_arr[(size_t)(i - 1) * kBlock];
+			if (!last_seg) ps_n = ps_arr[(size_t)(i - 1) * kBlock];
 			if (i <= len) {
-				const int x0 = rd.code(off + i - 1);  // seqa[i]
-				const float ps0 = last_seg ? NEG_INF : ps_arr[(size_t)i * kBlock];
-				float cs = cs_arr[(size_t)i * kBlock];
 				float eM0[N], eI0[N];
 #pragma unroll UN
 				for (int g = 0; g < N; ++g) {
@@ -150,7 +219,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 					if (live_of<STD>(nc, m, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + eI0[m], tab);
 					oldMp = M[m]; newMp = nM; D = NEG_INF;
 					M[m] = nM; I[m] = nI;
-					if (STORE) bw[((size_t)(c0 + m) * a.lmax + (i - 1)) * kBlock] = make_float2(nM, nI);
+					if (STORE) __stcs(&bw[((size_t)(c0 + m) * a.lmax + (i - 1)) * kBlock], make_float2(nM, nI));
 				}
 				// ---- columns m-1 .. 0 (:3545-3589)
 #pragma unroll UN
@@ -189,7 +258,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 						if (live_of<STD>(nc, g, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + eI0[g], tab);
 						M[g] = nM; I[g] = nI;
 						oldMp = oldMg; newMp = nM;
-						if (STORE) bw[((size_t)(c0 + g) * a.lmax + (i - 1)) * kBlock] = make_float2(nM, nI);
+						if (STORE) __stcs(&bw[((size_t)(c0 + g) * a.lmax + (i - 1)) * kBlock], make_float2(nM, nI));
 					}
 				}
 				if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // once per HMM f (:3604)
@@ -223,6 +292,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 	float2* bw = a.bw + (size_t)blockIdx.x * ((size_t)a.C * a.lmax) * kBlock + threadIdx.x;
 	float* sb = a.sb + (size_t)blockIdx.x * ((size_t)a.S * W) * kBlock + threadIdx.x;
 	if (!valid) len = 0;
+	const int x_term = rd.code(off + len);
 
 	// init silent_backward (:3479-3491): -inf, then the len+1 chain of skips
 	for (int j = 0; j < a.S; ++j)
@@ -240,7 +310,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 		const bool last = (j == a.S - 1);
 		const int kind = sg.kind;  // host-selected code path: 0 generic, 1 STD
 		const int nc = sg.nc;
-#define BWD_CASE(NCV, STDV) bwd_segment<NCV, STDV, STORE>(a, sm, sg, j, rd, off, len, lw, last, bw, sb)
+#define BWD_CASE(NCV, STDV) bwd_segment<NCV, STDV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb)
 		if (kind == 1) {
 			switch (nc) {
 				case 3: BWD_CASE(3, true); break;
@@ -265,6 +335,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 
 // ------------------------------------------------------------------------------------------
 // forward + posterior, one segment.  barcode_hmm.c:4199-4345
+// Mb/Ib of position i+1 (HBM), cs_arr[i+1] and ps_arr[i+1] are loaded one position ahead.
 // ------------------------------------------------------------------------------------------
 template <int NC, bool STD>
 __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
@@ -274,11 +345,12 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 {
 	constexpr int N = Cols<NC, STD>::N;
 	constexpr int UN = NC > 0 ? N : 1;
+	constexpr int NB = NC > 0 ? NC : 1;  // prefetch registers only on the unrolled paths
 	const int nc = NC > 0 ? NC : sg.nc;
 	const size_t W = (size_t)(a.lmax + 2);
 	float* cs_arr = sf + ((size_t)j * W) * kBlock;
 	const float* ps_arr = sf + ((size_t)(j - 1) * W) * kBlock;  // only dereferenced when j > 0
-	const float* tab = sm.tab;
+	const TabAddr tab = sm.tab;
 	const bool first_seg = (j == 0);
 	const int skip_live = sg.skip_live;
 
@@ -287,25 +359,43 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 		const int c0 = sg.colbase + f * nc;
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
 		const float* em = sm.emit + (size_t)c0 * kEmitRec;
+		const float2* bwc = bw + (size_t)c0 * a.lmax * kBlock;
 		float M[N], I[N];
+		float2 bn[NB];
 #pragma unroll UN
 		for (int g = 0; g < N; ++g) {
 			if (g < nc) { M[g] = NEG_INF; I[g] = NEG_INF; }
 		}
+		if (NC > 0) {
+#pragma unroll
+			for (int g = 0; g < NB; ++g) bn[g] = __ldcs(&bwc[((size_t)g * a.lmax) * kBlock]);
+		}
 		float TP = NEG_INF;
 		float ps1 = first_seg ? 0.0f : ps_arr[0];  // psilent[0]
+		SeqUp su;
+		su.init(rd, off, a.words);
+		float cs_n = cs_arr[(size_t)1 * kBlock];
+		float ps_n = first_seg ? NEG_INF : ps_arr[(size_t)1 * kBlock];
 		for (int i = 1; i <= lw; ++i) {
+			const int x = su.get();  // seqa[i]
+			float cs = cs_n;
+			const float ps0 = ps_n;
+			float2 bc[NB];
+			if (NC > 0) {
+				const int ip = (i < a.lmax) ? i : a.lmax - 1;  // position i+1, clamped to the scratch
+#pragma unroll
+				for (int g = 0; g < NB; ++g) { bc[g] = bn[g]; bn[g] = __ldcs(&bwc[((size_t)g * a.lmax + ip) * kBlock]); }
+			}
+			cs_n = cs_arr[(size_t)(i + 1) * kBlock];
+			if (!first_seg) ps_n = ps_arr[(size_t)(i + 1) * kBlock];
 			if (i <= len) {
-				const int x = rd.code(off + i - 1);  // seqa[i]
-				const float ps0 = first_seg ? NEG_INF : ps_arr[(size_t)i * kBlock];
-				float cs = cs_arr[(size_t)i * kBlock];
 				float P;
 				float oldMp, oldIp, newMp, D;
 				// ---- column 0 (:4218-4266)
 				{
 					const float* r = rec;
 					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
-					const float2 b = bw[((size_t)c0 * a.lmax + (i - 1)) * kBlock];
+					const float2 b = NC > 0 ? bc[0] : __ldcs(&bwc[(size_t)(i - 1) * kBlock]);
 					const float eM = em[x], eI = em[5 + x];
 					const bool lsm = live_of<STD>(nc, 0, F_SM, lv);
 					const bool lsi = live_of<STD>(nc, 0, F_SI, lv);
@@ -336,7 +426,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 						const float* rp = rec + p * kColRec;
 						const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
 						const uint32_t lp = STD ? 0u : __float_as_uint(rp[F_LIVE]);
-						const float2 b = bw[((size_t)(c0 + g) * a.lmax + (i - 1)) * kBlock];
+						const float2 b = NC > 0 ? bc[NC > 0 ? g : 0] : __ldcs(&bwc[((size_t)g * a.lmax + (i - 1)) * kBlock]);
 						const float eM = em[g * kEmitRec + x], eI = em[g * kEmitRec + 5 + x];
 						const float oldMg = M[g], oldIg = I[g];
 						float v; bool have;
@@ -371,7 +461,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				}
 				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
 				cs_arr[(size_t)i * kBlock] = cs;
-				post[((size_t)(i - 1) * a.H + h) * kBlock] = P;
+				__stcs(&post[((size_t)(i - 1) * a.H + h) * kBlock], P);
 				ps1 = ps0;
 			}
 		}
@@ -443,7 +533,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 #undef FWD_CASE
 	}
 	if (!valid) return;
-	const float* tab = sm.tab;
+	const TabAddr tab = sm.tab;
 	const float f_score = sf[((size_t)(a.S - 1) * W + len) * kBlock];  // (:4349)
 
 	// total_prob normalisation + bar_prob (:4354-4429); next_silent[0] is never reset.
@@ -516,6 +606,9 @@ __device__ __forceinline__ float post_exp(float x)
 
 __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 {
+	__shared__ int s_src[TDG_MAX_HMMS_DEV * kMaxSources];
+	for (int k = threadIdx.x; k < a.H * kMaxSources; k += kDpBlock) s_src[k] = a.dp_src[k];
+	__syncthreads();
 	const int slot = blockIdx.x * kDpBlock + threadIdx.x;
 	const int read = slot;
 	if (read >= a.n_reads) return;
@@ -534,6 +627,7 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 		// row 0: exp(-inf) = 0 everywhere
 		for (int s = 0; s < a.S; ++s) { segmax[s] = 0.0f; segarg[s] = a.seg[s].hmmbase; }
 		if (a.dp_structured) {
+			constexpr int CH = 8;  // HMMs per chunk: their row / previous-row loads are issued together
 			for (int i = 1; i <= len; ++i) {
 				float* row = post + ((size_t)(i - 1) * H) * kBlock;
 				const float* prow = post + ((size_t)(i - 2) * H) * kBlock;  // valid when i >= 2
@@ -543,24 +637,38 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 				for (int s = 0; s < a.S; ++s) {
 					const int hb = a.seg[s].hmmbase, nh = a.seg[s].nh;
 					float cm = -1.0f; int ca = hb;
-					for (int f = 0; f < nh; ++f) {
-						const int j = hb + f;
-						float best = -1.0f; int arg = -1;
-						for (int k = 0; k < kMaxSources; ++k) {
-							const int src = a.dp_src[j * kMaxSources + k];
-							if (src == INT32_MIN) break;
-							float v; int av;
-							if (src < 0) { v = segmax[-src - 1]; av = segarg[-src - 1]; }
-							else { v = (i >= 2) ? prow[(size_t)src * kBlock] : 0.0f; av = src; }
-							if (v > best) { best = v; arg = av; }
+					for (int f0 = 0; f0 < nh; f0 += CH) {
+						float pv[CH], sv[CH];
+#pragma unroll
+						for (int k = 0; k < CH; ++k) {
+							const int j = hb + f0 + k;
+							if (f0 + k < nh) {
+								pv[k] = __ldcs(&row[(size_t)j * kBlock]);
+								sv[k] = (i >= 2) ? prow[(size_t)j * kBlock] : 0.0f;
+							}
 						}
-						const float self = (i >= 2) ? prow[(size_t)j * kBlock] : 0.0f;
-						float mx; int mv;
-						if (self >= best) { mx = self; mv = j; } else { mx = best; mv = arg; }
-						const float nd = post_exp(row[(size_t)j * kBlock]) + mx;
-						row[(size_t)j * kBlock] = nd;
-						prow_path[(size_t)j * kBlock] = (uint8_t)mv;
-						if (nd > cm) { cm = nd; ca = j; }
+#pragma unroll
+						for (int k = 0; k < CH; ++k) {
+							const int j = hb + f0 + k;
+							if (f0 + k < nh) {
+								float best = -1.0f; int arg = -1;
+								for (int q = 0; q < kMaxSources; ++q) {
+									const int src = s_src[j * kMaxSources + q];
+									if (src == INT32_MIN) break;
+									float v; int av;
+									if (src < 0) { v = segmax[-src - 1]; av = segarg[-src - 1]; }
+									else { v = (i >= 2) ? prow[(size_t)src * kBlock] : 0.0f; av = src; }
+									if (v > best) { best = v; arg = av; }
+								}
+								const float self = sv[k];
+								float mx; int mv;
+								if (self >= best) { mx = self; mv = j; } else { mx = best; mv = arg; }
+								const float nd = post_exp(pv[k]) + mx;
+								row[(size_t)j * kBlock] = nd;
+								__stcs(&prow_path[(size_t)j * kBlock], (uint8_t)mv);
+								if (nd > cm) { cm = nd; ca = j; }
+							}
+						}
 					}
 					nsegmax[s] = cm; nsegarg[s] = ca;
 				}
