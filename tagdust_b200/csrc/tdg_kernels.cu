@@ -38,6 +38,9 @@ constexpr int TDG_MAX_HMMS_DEV = 255;
 // in its mantissa (0 <= x < 2^23), so its bit pattern << 2 plus a pre-offset shared-memory
 // base is the byte address of tab[(int)x]; no F2I (XU pipe) on the hot path.
 // ------------------------------------------------------------------------------------------
+constexpr int kPrefetchDist = 5;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 typedef uint32_t TabAddr;  // shared-memory byte address of the table minus (0x4B000000 << 2)
 
 __device__ __forceinline__ TabAddr make_tab_addr(const float* tab)
@@ -197,6 +200,10 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 			const float ps0 = ps_n;
 			cs_n = cs_arr[(size_t)(i - 1) * kBlock];
 			if (!last_seg) ps_n = ps_arr[(size_t)(i - 1) * kBlock];
+			if (i > kPrefetchDist) {  // pull the silent-state lines of iteration i-kPrefetchDist towards L1
+				prefetch_l1(&cs_arr[(size_t)(i - kPrefetchDist) * kBlock]);
+				if (!last_seg) prefetch_l1(&ps_arr[(size_t)(i - kPrefetchDist) * kBlock]);
+			}
 			if (i <= len) {
 				float eM0[N], eI0[N];
 #pragma unroll UN
