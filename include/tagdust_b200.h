@@ -166,6 +166,10 @@ int  tdg_batch_append_records(tdg_batch* b, int n, const void* const* records,
                               size_t seq_off, size_t len_off);
 int  tdg_batch_size(const tdg_batch* b);
 
+/* Host-only: how a batch of n_reads is split over n_devices (contiguous, 32-read-tile aligned,
+ * keeps output order = input order like the reference's static slices, barcode_hmm.c:1911-1922). */
+int  tdg_plan_shards(int n_reads, int n_devices, int32_t* first, int32_t* count);
+
 /* ---- the hot path ----------------------------------------------------------------- */
 /* Asynchronous: H2D copies, kernels and D2H copies are queued on the batch's streams
  * (reads sharded contiguously over the context's devices); returns immediately. */

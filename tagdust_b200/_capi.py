@@ -117,6 +117,7 @@ PROTOTYPES = {
     "tdg_batch_append_codes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tdg_batch_append_records": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]),
     "tdg_batch_size": (C.c_int, [C.c_void_p]),
+    "tdg_plan_shards": (C.c_int, [C.c_int, C.c_int, c_int32_p, c_int32_p]),
     "tdg_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RunParamsC), C.c_void_p]),
     "tdg_wait": (C.c_int, [C.c_void_p, C.POINTER(ResultC)]),
     "tdg_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RunParamsC), C.c_void_p, C.POINTER(ResultC)]),

@@ -565,18 +565,26 @@ extern "C" int tdg_batch_append_records(tdg_batch* b, int n, const void* const* 
 	return TDG_OK;
 }
 
+extern "C" int tdg_plan_shards(int n_reads, int n_devices, int32_t* first, int32_t* count)
+{
+	if (n_reads < 0 || n_devices < 1 || !first || !count) return fail(TDG_EINVAL, "bad argument");
+	const int tiles = (n_reads + 31) / 32;
+	const int per = (tiles + n_devices - 1) / n_devices * 32;
+	int f = 0;
+	for (int k = 0; k < n_devices; k++) {
+		first[k] = std::min(f, n_reads);
+		count[k] = std::max(0, std::min(per, n_reads - first[k]));
+		f += per;
+	}
+	return TDG_OK;
+}
+
 static void assign_shards(tdg_batch* b)
 {
 	const int nd = (int)b->shard.size();
-	const int tiles = (b->n + 31) / 32;
-	const int per = (tiles + nd - 1) / nd * 32;
-	int first = 0;
-	for (int k = 0; k < nd; k++) {
-		Shard& s = b->shard[k];
-		s.first = std::min(first, b->n);
-		s.n = std::max(0, std::min(per, b->n - s.first));
-		first += per;
-	}
+	std::vector<int32_t> first(nd), count(nd);
+	tdg_plan_shards(b->n, nd, first.data(), count.data());
+	for (int k = 0; k < nd; k++) { b->shard[k].first = first[k]; b->shard[k].n = count[k]; }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -41,3 +41,175 @@ def test_label_parity_vs_oracle(gpu_ctx, oracle, ref, name):
     rep = compare(gpu, ora, lens, MODE_GET_LABEL, name)
     batch.close(); model.close(); ref.model_free(mb); ref.param_free(p)
     assert all(v == 0 for v in rep.values()), f"{name}: mismatches {rep}"
+
+
+def run_gpu(gpu_ctx, desc, codes, lens, mode, **kw):
+    max_len = int(lens.max()) if len(lens) else 1
+    model = gpu_ctx.model(desc, max(max_len, 1))
+    batch = gpu_ctx.batch(max(len(lens), 1), max(max_len, 1))
+    if len(lens):
+        batch.append(codes, lens)
+    out = gpu_ctx.run_phmm(model, batch, mode, **kw)
+    batch.close(); model.close()
+    return out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_vectors(gpu_ctx, name):
+    """CUDA path vs the committed vectors produced by the UNMODIFIED reference."""
+    from test_oracle import load_golden
+    z, desc = load_golden(name)
+    lens = z["lens"]
+    gpu = run_gpu(gpu_ctx, desc, z["codes"], lens, MODE_GET_LABEL, threshold=float(z["threshold"]), minlen=16, dust=100)
+    for k in SCORE_KEYS:
+        assert np.array_equal(bits(gpu[k]), bits(z[k])), k
+    for k in ("read_type", "barcode", "fingerprint"):
+        assert np.array_equal(gpu[k], z[k]), k
+    for r in range(len(lens)):
+        assert np.array_equal(gpu["labels"][r, : lens[r] + 1], z["labels"][r, : lens[r] + 1])
+    # extracted flag <-> the reference rewrote the sequence (spacer 65 appears or read kept whole)
+    assert np.array_equal(gpu["extracted"].astype(bool), z["read_type"] == 0) or (z["read_type"] == 6).any()
+
+
+def test_get_prob_mode(gpu_ctx, oracle, ref):
+    codes, lens, _ = make_case_reads("f_s_b_r", 700, seed=4)
+    p, mb, desc = build_ref_model(ref, "f_s_b_r")
+    ora = oracle.run(desc, MODE_GET_PROB, codes, lens, threads=8)
+    for want_labels in (True, False):
+        gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_PROB, want_labels=want_labels)
+        for k in SCORE_KEYS:
+            assert np.array_equal(bits(gpu[k]), bits(ora[k])), k
+        if want_labels:
+            for r in range(len(lens)):
+                assert np.array_equal(gpu["labels"][r, : lens[r] + 1], ora["labels"][r, : lens[r] + 1])
+    ref.model_free(mb); ref.param_free(p)
+
+
+def test_calibration_model_and_reads(gpu_ctx, oracle, ref):
+    """Threshold calibration path (calibrateQ.c): reads emitted by the reference's emitters from the
+    edited model, scored in MODE_GET_PROB.  Emitted reads are longer than the average length."""
+    p, mb, desc0 = build_ref_model(ref, "b4_r", avg_len=26, max_len=400)
+    ref.model_calibration_edit(mb, p)
+    codes, lens = ref.emit(mb, 300, 300, 26, 42, 512)
+    ref.model_free(mb)
+    mb = ref.model_new(p, average_length=26.0, max_seq_len=int(lens.max()))
+    desc = ref.flatten(mb, p)
+    want = ref.run_phmm(mb, p, 4, codes, lens)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_PROB, want_labels=False)
+    assert np.array_equal(bits(gpu["mapq"]), bits(want["mapq"]))
+    assert np.array_equal(bits(gpu["bar_prob"]), bits(want["bar_prob"].astype(np.float32)))
+    ref.model_free(mb); ref.param_free(p)
+
+
+@pytest.mark.parametrize("threads", [1, 8])
+def test_arch_compare(gpu_ctx, oracle, ref, threads):
+    names = ["b4_r", "p_b_r_p", "o_b_s_r", "g_b2_r"]
+    codes, lens, _ = make_case_reads("b4_r", 1000, seed=9, read_len=40)
+    built = [build_ref_model(ref, n, avg_len=40, max_len=48, threads=threads) for n in names]
+    post_ref = ref.run_arch_comp([b[1] for b in built], built[0][0], codes, lens)
+    models = [gpu_ctx.model(b[2], 48) for b in built]
+    batch = gpu_ctx.batch(len(lens), 48)
+    batch.append(codes, lens)
+    bs, post = gpu_ctx.arch_compare(models, batch, num_threads=threads)
+    for k, b in enumerate(built):
+        assert np.array_equal(bits(bs[k]), bits(ref.backward_scores(b[1], codes, lens))), names[k]
+    assert np.array_equal(bits(post), bits(post_ref))
+    assert int(np.argmax(post)) == 0
+    batch.close()
+    for m in models:
+        m.close()
+    for b in built:
+        ref.model_free(b[1]); ref.param_free(b[0])
+
+
+def test_window_start_end(gpu_ctx, oracle, ref):
+    codes, lens, _ = make_case_reads("b4_r", 500, seed=3, len_jitter=0)
+    c = CASES["b4_r"]
+    p = ref.param_new(c["segments"], threshold=1.0, minlen=5, dust=100, matchstart=2, matchend=22)
+    mb = ref.model_new(p, average_length=20.0, max_seq_len=30)
+    desc = ref.flatten(mb, p)
+    sh = np.zeros_like(codes); sh[:, 2:] = codes[:, :-2]; sh[:, :2] = 3
+    lens2 = lens + 2
+    ora = oracle.run(desc, MODE_GET_LABEL, sh, lens2, threshold=1.0, minlen=5, dust=100, matchstart=2, matchend=22, threads=4)
+    gpu = run_gpu(gpu_ctx, desc, sh, lens2, MODE_GET_LABEL, threshold=1.0, minlen=5, dust=100, matchstart=2, matchend=22)
+    for k in SCORE_KEYS:
+        assert np.array_equal(bits(gpu[k]), bits(ora[k])), k
+    for k in ("read_type", "barcode", "fingerprint"):
+        assert np.array_equal(gpu[k], ora[k]), k
+    ref.model_free(mb); ref.param_free(p)
+
+
+def test_ragged_short_and_ambiguous_reads(gpu_ctx, oracle, ref):
+    """Edge cases: lengths from the shortest the model can emit up to the maximum, N-rich reads,
+    homopolymers (dust), thresholds that reject everything / nothing, minlen larger than the read."""
+    rng = np.random.default_rng(8)
+    p, mb, desc = build_ref_model(ref, "b4_r", max_len=120)
+    n = 1200
+    lens = rng.integers(4, 121, size=n).astype(np.int32)
+    lens[:8] = [4, 5, 6, 7, 8, 120, 120, 119]
+    stride = 128
+    codes = np.zeros((n, stride), np.uint8)
+    for r in range(n):
+        codes[r, : lens[r]] = rng.integers(0, 4, size=lens[r])
+    codes[100:200] = np.where(rng.random((100, stride)) < 0.5, 4, codes[100:200])   # N-rich
+    for r in range(200, 260):
+        codes[r, : lens[r]] = rng.integers(0, 4)                                     # homopolymers
+    for r in range(n):
+        codes[r, lens[r]:] = 0
+    for thr, minlen, dust in ((0.0, 16, 100), (39.0, 16, 100), (1.5, 200, 0), (1.5, 1, 5)):
+        ora = oracle.run(desc, MODE_GET_LABEL, codes, lens, threshold=thr, minlen=minlen, dust=dust, threads=8)
+        gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=thr, minlen=minlen, dust=dust)
+        rep = compare(gpu, ora, lens, MODE_GET_LABEL, "edge")
+        assert all(v == 0 for v in rep.values()), (thr, minlen, dust, rep)
+    ref.model_free(mb); ref.param_free(p)
+
+
+def test_empty_batch(gpu_ctx, ref):
+    p, mb, desc = build_ref_model(ref, "b4_r")
+    out = run_gpu(gpu_ctx, desc, np.zeros((0, 32), np.uint8), np.zeros(0, np.int32), MODE_GET_LABEL, threshold=1.0)
+    assert out["mapq"].shape == (0,)
+    ref.model_free(mb); ref.param_free(p)
+
+
+def test_too_long_read_is_rejected(gpu_ctx, ref):
+    from tagdust_b200.api import TagdustError
+    p, mb, desc = build_ref_model(ref, "b4_r")
+    model = gpu_ctx.model(desc, 30)
+    batch = gpu_ctx.batch(4, 64)
+    codes = np.zeros((1, 64), np.uint8)
+    batch.append(codes, np.array([50], np.int32))
+    with pytest.raises(TagdustError):
+        gpu_ctx.run_phmm(model, batch, MODE_GET_LABEL, threshold=1.0)
+    batch.close(); model.close(); ref.model_free(mb); ref.param_free(p)
+
+
+def test_multi_wave_and_sampled_parity_full_size(gpu_ctx, oracle):
+    """BASELINE cfg2 at full shape (150 nt, 48 barcodes), several waves of 75 776 reads:
+    size-independent properties + oracle parity on a random sample of the reads."""
+    from tagdust_b200 import synth
+    from tagdust_b200.api import compile_architecture
+    from refharness import background_logp
+    from cases import TAGS6_ED3
+    tags = TAGS6_ED3[:48]
+    desc = compile_architecture(["B:" + ",".join(tags), "R:N"], background_logp((2.5e6, 2.5e6, 2.5e6, 2.5e6, 1.0)), 150.0, 150)
+    n = 75776 * 2 + 1234
+    codes, lens, truth = synth.make_reads_fast(n, 150, tags, error_rate=0.01, random_frac=0.05, seed=77)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.5, minlen=16, dust=100)
+    # properties: forward == backward likelihood up to float noise; labels monotone in segment; truth recovered
+    assert np.all(np.abs(gpu["f_score"] - gpu["b_score"]) < 2e-2)
+    ok = gpu["read_type"] == 0
+    assert ok[truth >= 0].mean() > 0.99
+    assert ((gpu["barcode"][ok] & 0xFFFF) == truth[ok]).mean() > 0.995
+    lab = gpu["labels"][:, 1:151]
+    seg = (np.asarray(desc.label)[lab] & 0xFFFF)
+    assert np.all(np.diff(seg.astype(np.int32), axis=1) >= 0)          # segments never go backwards
+    # idempotence: same batch again -> identical bits
+    gpu2 = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.5, minlen=16, dust=100)
+    for k in SCORE_KEYS:
+        assert np.array_equal(bits(gpu[k]), bits(gpu2[k]))
+    # oracle parity on a sample spread over all waves (incl. the ragged last wave)
+    idx = np.concatenate([np.arange(0, n, 997), np.arange(n - 40, n)])
+    ora = oracle.run(desc, MODE_GET_LABEL, codes[idx], lens[idx], threshold=1.5, minlen=16, dust=100, threads=8)
+    sub = {k: v[idx] for k, v in gpu.items()}
+    rep = compare(sub, ora, lens[idx], MODE_GET_LABEL, "cfg2")
+    assert all(v == 0 for v in rep.values()), rep
