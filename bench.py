@@ -172,17 +172,14 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
     import torch
-    import torch.distributed as dist
+    from tagdust_b200 import dist_util
     from tagdust_b200.api import MODE_GET_LABEL, Context, compile_architecture
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = dist_util.env_rank()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist_util.init("nccl")
 
     segs, tags = architecture()
     desc = compile_architecture(segs, background(), float(READ_LEN), READ_LEN)
@@ -195,10 +192,7 @@ def run_gpu_arm(args):
     batches = [ctx.batch(n_reads, READ_LEN) for _ in range(2)]
     kw = dict(threshold=THRESHOLD, minlen=16, dust=100)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = dist_util.barrier
 
     # ---- (1) kernel-only: inputs resident in HBM, CUDA events on the launching stream
     batches[0].append(codes, lens)
@@ -253,10 +247,9 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- reduce over ranks (max time), rank 0 prints
-    t = torch.tensor([ms_total, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms = dist_util.max_over_ranks([ms_total, e2e_s * 1000.0])
+    tallies = dist_util.merge_tallies(np.bincount(res["read_type"], minlength=7))   # merged on the host side
+    assigned_ok, n_model = [int(x) for x in dist_util.merge_tallies([assigned_ok, n_model])]
     total_reads = n_reads * world
     value = total_reads * args.steps / (ms_total / 1000.0)
     e2e_value = total_reads * args.steps / (e2e_ms / 1000.0)
@@ -297,7 +290,7 @@ def run_gpu_arm(args):
                 "peak_gbs": pk.get("hbm_gbs"), "what": "Mb/Ib scratch write+read over k_backward+k_forward time"},
         "kernels_ms": prof,
         "check": {"reads_with_true_barcode_assigned": assigned_ok, "model_reads": n_model,
-                  "read_type_counts": np.bincount(res["read_type"], minlength=7).tolist()},
+                  "read_type_counts": tallies.tolist()},
     }
     line["roofline_whole_path"]["frac"] = line["roofline_whole_path"]["achieved"] / fp32_peak
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -313,8 +306,7 @@ def run_gpu_arm(args):
         b.close()
     model.close()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    dist_util.finalize()
 
 
 def main():

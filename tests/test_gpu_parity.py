@@ -214,3 +214,20 @@ def test_multi_wave_and_sampled_parity_full_size(gpu_ctx, oracle):
     sub = {k: v[idx] for k, v in gpu.items()}
     rep = compare(sub, ora, lens[idx], MODE_GET_LABEL, "cfg2")
     assert all(v == 0 for v in rep.values()), rep
+
+
+def test_two_device_context_matches_single(oracle, ref):
+    """Sharding over the GPUs of one context: contiguous tile-aligned shards, output order = input order."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tagdust_b200.api import Context
+    ctx = Context(2)
+    assert ctx.device_count == 2
+    codes, lens, _ = make_case_reads("b_b_r", 3000, seed=12)
+    p, mb, desc = build_ref_model(ref, "b_b_r")
+    ora = oracle.run(desc, MODE_GET_LABEL, codes, lens, threshold=1.5, minlen=16, dust=100, threads=8)
+    gpu = run_gpu(ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.5, minlen=16, dust=100)
+    rep = compare(gpu, ora, lens, MODE_GET_LABEL, "2gpu")
+    assert all(v == 0 for v in rep.values()), rep
+    ctx.close(); ref.model_free(mb); ref.param_free(p)
