@@ -164,7 +164,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -301,7 +301,7 @@ def run_gpu_arm(args):
         line["cpu_baseline"] = {"value": cpu_value, "unit": "reads/s", "cores": threads, "kind": kind,
                                 "sample": f"{n_cpu} reads of the same workload, run_pHMM(MODE_GET_LABEL), {threads} pthreads, {times[0]:.1f} s"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     for b in batches:
         b.close()
     model.close()
@@ -309,7 +309,24 @@ def run_gpu_arm(args):
     dist_util.finalize()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints to fd 1
+    (e.g. NCCL's version banner) has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
