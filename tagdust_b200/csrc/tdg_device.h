@@ -81,6 +81,7 @@ struct KArgs {
 	float*  sf;                // [cta][S*(lmax+2)][kBlock] silent_forward
 	float*  post;              // [cta][lmax*H][kBlock] posterior matrix rows 1..L
 	float*  tp;                // [cta][H][kBlock] total_prob
+	uint32_t* prange;          // [cta][H][kBlock] (last<<16)|first position with posterior >= -104
 	uint8_t* path;             // [cta][lmax*H][kBlock]
 	// per-read outputs (device)
 	float* b_score; float* f_score; float* r_score; float* bar_prob; float* mapq;

@@ -386,7 +386,7 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 	const size_t smem = decode_smem_bytes((int)hm.blob.size());
 	const size_t W = (size_t)max_len + 2;
 	m->slot_bytes_bwd = (size_t)hm.S * W * 4;
-	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 4 +
+	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
 	                     (size_t)max_len * hm.H;
 	m->dev.resize(ctx->devs.size());
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
@@ -621,6 +621,7 @@ static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool
 	if (full) {
 		a.sf = (float*)take(slots * hm.S * W * 4);
 		a.tp = (float*)take(slots * hm.H * 4);
+		a.prange = (uint32_t*)take(slots * hm.H * 4);
 		a.post = (float*)take(slots * (size_t)m->max_len * hm.H * 4);
 		a.path = (uint8_t*)take(slots * (size_t)m->max_len * hm.H);
 		a.bw = (float2*)take(slots * (size_t)hm.C * m->max_len * 8);
@@ -630,7 +631,7 @@ static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool
 static size_t scratch_need(const tdg_model* m, const DeviceCtx& d, bool full)
 {
 	const size_t slots = (size_t)d.ctas * kBlock;
-	return slots * (full ? m->slot_bytes_full : m->slot_bytes_bwd) + 8 * 256;
+	return slots * (full ? m->slot_bytes_full : m->slot_bytes_bwd) + 10 * 256;
 }
 
 // Queue all waves of one shard on `stream`.  Returns kernel launches queued (<0 on error).

@@ -348,7 +348,8 @@ template <int NC, bool STD>
 __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, float B,
                                             const float2* __restrict__ bw, float* __restrict__ sf,
-                                            float* __restrict__ post, float* __restrict__ tp)
+                                            float* __restrict__ post, float* __restrict__ tp,
+                                            uint32_t* __restrict__ prange)
 {
 	constexpr int N = Cols<NC, STD>::N;
 	constexpr int UN = NC > 0 ? N : 1;
@@ -378,6 +379,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 			for (int g = 0; g < NB; ++g) bn[g] = __ldcs(&bwc[((size_t)g * a.lmax) * kBlock]);
 		}
 		float TP = NEG_INF;
+		int pfirst = 0xFFFF, plast = 0;  // positions whose posterior is >= -104 (exp != 0), for k_label
 		float ps1 = first_seg ? 0.0f : ps_arr[0];  // psilent[0]
 		SeqUp su;
 		su.init(rd, off, a.words);
@@ -469,10 +471,12 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
 				cs_arr[(size_t)i * kBlock] = cs;
 				__stcs(&post[((size_t)(i - 1) * a.H + h) * kBlock], P);
+				if (!(P < -104.0f)) { plast = i; pfirst = min(pfirst, i); }
 				ps1 = ps0;
 			}
 		}
 		tp[(size_t)h * kBlock] = TP;
+		prange[(size_t)h * kBlock] = ((uint32_t)plast << 16) | (uint32_t)pfirst;
 	}
 }
 
@@ -502,6 +506,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 	float* sf = a.sf + (size_t)blockIdx.x * ((size_t)a.S * W) * kBlock + threadIdx.x;
 	float* post = a.post + (size_t)blockIdx.x * ((size_t)a.lmax * a.H) * kBlock + threadIdx.x;
 	float* tp = a.tp + (size_t)blockIdx.x * ((size_t)a.H) * kBlock + threadIdx.x;
+	uint32_t* prange = a.prange + (size_t)blockIdx.x * ((size_t)a.H) * kBlock + threadIdx.x;
 	const float B = valid ? a.b_score[read] : 0.0f;
 
 	// init silent_forward (:4166-4175)
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 		const SegInfo sg = a.seg[j];
 		const int kind = sg.kind;
 		const int nc = sg.nc;
-#define FWD_CASE(NCV, STDV) fwd_segment<NCV, STDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sf, post, tp)
+#define FWD_CASE(NCV, STDV) fwd_segment<NCV, STDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sf, post, tp, prange)
 		if (kind == 1) {
 			switch (nc) {
 				case 3: FWD_CASE(3, true); break;
@@ -614,9 +619,11 @@ __device__ __forceinline__ float post_exp(float x)
 __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 {
 	__shared__ int s_src[TDG_MAX_HMMS_DEV * kMaxSources];
-	for (int k = threadIdx.x; k < a.H * kMaxSources; k += kDpBlock) s_src[k] = a.dp_src[k];
+	extern __shared__ float dsm[];  // structured path: D row [H][blockDim] floats, then posterior ranges [H][blockDim] u32
+	const int bs = blockDim.x;
+	for (int k = threadIdx.x; k < a.H * kMaxSources; k += bs) s_src[k] = a.dp_src[k];
 	__syncthreads();
-	const int slot = blockIdx.x * kDpBlock + threadIdx.x;
+	const int slot = blockIdx.x * bs + threadIdx.x;
 	const int read = slot;
 	if (read >= a.n_reads) return;
 	const int cta = slot / kBlock, t = slot % kBlock;
@@ -631,55 +638,72 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 	if (a.want_labels) {
 		float segmax[kMaxSegments];
 		int segarg[kMaxSegments];
+		int move = -1;
 		// row 0: exp(-inf) = 0 everywhere
 		for (int s = 0; s < a.S; ++s) { segmax[s] = 0.0f; segarg[s] = a.seg[s].hmmbase; }
 		if (a.dp_structured) {
-			constexpr int CH = 8;  // HMMs per chunk: their row / previous-row loads are issued together
+			// The DP row lives in shared memory and is updated in place from the highest HMM index
+			// down (every predecessor of j has a lower index, so it still holds row i-1).  Posterior
+			// entries outside [first,last] of their HMM (k_forward's prange) are < -104 and exp to
+			// exactly 0: they are neither loaded nor exponentiated.
+			constexpr int CH = 8;
+			float* D = dsm + threadIdx.x;
+			uint32_t* rng = (uint32_t*)(dsm + (size_t)H * bs) + threadIdx.x;
+			const uint32_t* prange = a.prange + (size_t)cta * H * kBlock + t;
+			for (int j = 0; j < H; ++j) { D[(size_t)j * bs] = 0.0f; rng[(size_t)j * bs] = prange[(size_t)j * kBlock]; }
 			for (int i = 1; i <= len; ++i) {
-				float* row = post + ((size_t)(i - 1) * H) * kBlock;
-				const float* prow = post + ((size_t)(i - 2) * H) * kBlock;  // valid when i >= 2
+				const float* row = post + ((size_t)(i - 1) * H) * kBlock;
 				uint8_t* prow_path = path + ((size_t)(i - 1) * H) * kBlock;
 				float nsegmax[kMaxSegments];
 				int nsegarg[kMaxSegments];
-				for (int s = 0; s < a.S; ++s) {
+				for (int s = a.S - 1; s >= 0; --s) {
 					const int hb = a.seg[s].hmmbase, nh = a.seg[s].nh;
 					float cm = -1.0f; int ca = hb;
-					for (int f0 = 0; f0 < nh; f0 += CH) {
-						float pv[CH], sv[CH];
+					for (int f1 = nh; f1 > 0; f1 -= CH) {
+						const int f0 = f1 > CH ? f1 - CH : 0;
+						float pv[CH];
 #pragma unroll
 						for (int k = 0; k < CH; ++k) {
-							const int j = hb + f0 + k;
-							if (f0 + k < nh) {
-								pv[k] = __ldcs(&row[(size_t)j * kBlock]);
-								sv[k] = (i >= 2) ? prow[(size_t)j * kBlock] : 0.0f;
+							const int f = f1 - 1 - k;
+							if (f >= f0) {
+								const int j = hb + f;
+								const uint32_t r = rng[(size_t)j * bs];
+								pv[k] = (i >= (int)(r & 0xFFFFu) && i <= (int)(r >> 16)) ? __ldcs(&row[(size_t)j * kBlock]) : NEG_INF;
 							}
 						}
 #pragma unroll
 						for (int k = 0; k < CH; ++k) {
-							const int j = hb + f0 + k;
-							if (f0 + k < nh) {
+							const int f = f1 - 1 - k;
+							if (f >= f0) {
+								const int j = hb + f;
 								float best = -1.0f; int arg = -1;
 								for (int q = 0; q < kMaxSources; ++q) {
 									const int src = s_src[j * kMaxSources + q];
 									if (src == INT32_MIN) break;
 									float v; int av;
 									if (src < 0) { v = segmax[-src - 1]; av = segarg[-src - 1]; }
-									else { v = (i >= 2) ? prow[(size_t)src * kBlock] : 0.0f; av = src; }
+									else { v = D[(size_t)src * bs]; av = src; }
 									if (v > best) { best = v; arg = av; }
 								}
-								const float self = sv[k];
+								const float self = D[(size_t)j * bs];
 								float mx; int mv;
 								if (self >= best) { mx = self; mv = j; } else { mx = best; mv = arg; }
 								const float nd = post_exp(pv[k]) + mx;
-								row[(size_t)j * kBlock] = nd;
+								D[(size_t)j * bs] = nd;
 								__stcs(&prow_path[(size_t)j * kBlock], (uint8_t)mv);
-								if (nd > cm) { cm = nd; ca = j; }
+								if (nd >= cm) { cm = nd; ca = j; }  // descending scan: >= leaves the first (lowest) maximum
 							}
 						}
 					}
 					nsegmax[s] = cm; nsegarg[s] = ca;
 				}
 				for (int s = 0; s < a.S; ++s) { segmax[s] = nsegmax[s]; segarg[s] = nsegarg[s]; }
+			}
+			// final argmax, first max wins (:4494-4501)
+			float mx = -1.0f;
+			for (int j = 0; j < H; ++j) {
+				const float v = D[(size_t)j * bs];
+				if (v > mx) { mx = v; move = j; }
 			}
 		} else {
 			// generic O(L*H^2) form, verbatim tie rules (:4453-4464)
@@ -699,10 +723,7 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 					prow_path[(size_t)j * kBlock] = (uint8_t)mv;
 				}
 			}
-		}
-		// final argmax, first max wins (:4494-4501)
-		int move = -1;
-		{
+			// final argmax, first max wins (:4494-4501)
 			float mx = -1.0f;
 			for (int j = 0; j < H; ++j) {
 				const float v = (len >= 1) ? post[((size_t)(len - 1) * H + j) * kBlock] : 0.0f;
@@ -810,6 +831,8 @@ int kernels_configure(int smem_bytes)
 	if (e != cudaSuccess) return (int)e;
 	e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(k_label, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	if (e != cudaSuccess) return (int)e;
 	return 0;
 }
 
@@ -831,8 +854,14 @@ int launch_forward(const KArgs& a, int ctas, void* stream)
 int launch_label(const KArgs& a, int ctas_decode, void* stream)
 {
 	const int threads = ctas_decode * kBlock;
-	const int ctas = (threads + kDpBlock - 1) / kDpBlock;
-	k_label<<<ctas, kDpBlock, 0, (cudaStream_t)stream>>>(a);
+	int bs = kDpBlock;
+	size_t smem = 0;
+	if (a.dp_structured) {
+		while (bs > 32 && (size_t)a.H * bs * 8 > 100 * 1024) bs >>= 1;  // keep >= 2 CTAs per SM
+		smem = (size_t)a.H * bs * 8;
+	}
+	const int ctas = (threads + bs - 1) / bs;
+	k_label<<<ctas, bs, smem, (cudaStream_t)stream>>>(a);
 	return (int)cudaGetLastError();
 }
 
