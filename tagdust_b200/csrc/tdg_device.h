@@ -53,7 +53,8 @@ struct SegInfo {
 	int32_t hmmbase;   // first global HMM
 	float   skip;      // model->skip
 	int32_t skip_live; // skip != -inf
-	int32_t kind;      // code path: 0 generic (runtime live masks), 1 STD column pattern
+	int32_t kind;      // code path: 0 generic (runtime live masks), 1 STDU (standard pattern, uniform scalars)
+	float   ta, tb, tb2, tc, td;  // STDU transition scalars (see trv<> in tdg_kernels.cu)
 };
 
 // Everything a kernel needs that is not in the model blob (passed by value).

@@ -270,18 +270,36 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 			emit[(size_t)c * kEmitRec + 5 + k] = d->i_emit[c * 5 + k];
 		}
 	}
-	// STD pattern check per segment: every term the pattern calls dead must be -inf
+	// STDU check per segment (kernel code path 1): the standard liveness pattern, the five
+	// transition scalars shared by every HMM of the segment, +0 for DM(n-2) and MSKIP(n-1), and
+	// one insert-emission row for all columns.  Everything compared bit for bit.
+	auto same = [](float x, float y) { return memcmp(&x, &y, 4) == 0; };
 	for (int s = 0; s < S; s++) {
 		SegInfo& g = hm.seg[s];
+		g.ta = g.tb = g.tb2 = g.tc = g.td = 0.0f;
 		if (g.nc < 3 || g.nc > 8) continue;
+		const float* r0 = rec + (size_t)g.colbase * kColRec;
+		const float* e0 = emit + (size_t)g.colbase * kEmitRec;
+		const float ta = r0[F_MM], tb = r0[F_MI], tc = r0[F_II], td = r0[F_IM];
+		const float tb2 = (r0 + (size_t)(g.nc - 2) * kColRec)[F_MI];
 		bool ok = true;
 		for (int f = 0; f < g.nh && ok; f++)
 			for (int col = 0; col < g.nc && ok; col++) {
-				const float* r = rec + (size_t)(g.colbase + f * g.nc + col) * kColRec;
+				const int c = g.colbase + f * g.nc + col;
+				const float* r = rec + (size_t)c * kColRec;
+				const float* e = emit + (size_t)c * kEmitRec;
 				for (int k = 0; k < 11; k++)
-					if (!std_live(g.nc, col, k) && !is_ninf(r[k])) { ok = false; break; }
+					if (!std_live(g.nc, col, k) && !is_ninf(r[k])) ok = false;
+				for (int k = 0; k < 5; k++)
+					if (!same(e[5 + k], e0[5 + k])) ok = false;
+				if (col == g.nc - 1) { if (!same(r[F_MSKIP], 0.0f)) ok = false; continue; }
+				if (!same(r[F_MM], ta) || !same(r[F_II], tc) || !same(r[F_IM], td)) ok = false;
+				if (!same(r[F_MI], col == g.nc - 2 ? tb2 : tb)) ok = false;
+				if (col <= g.nc - 3 && !same(r[F_MD], tb)) ok = false;
+				if (col >= 1 && col <= g.nc - 3 && (!same(r[F_DD], tc) || !same(r[F_DM], td))) ok = false;
+				if (col == g.nc - 2 && !same(r[F_DM], 0.0f)) ok = false;
 			}
-		if (ok) { g.kind = 1; hm.std_segments++; }
+		if (ok) { g.kind = 1; g.ta = ta; g.tb = tb; g.tb2 = tb2; g.tc = tc; g.td = td; hm.std_segments++; }
 	}
 	// labels, types
 	hm.label.assign(d->label, d->label + H);

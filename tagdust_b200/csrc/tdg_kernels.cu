@@ -50,10 +50,10 @@ __device__ __forceinline__ TabAddr make_tab_addr(const float* tab)
 
 __device__ __forceinline__ float LS(float a, float b, TabAddr tab)
 {
+	// max - min == |a - b| bit for bit (IEEE negation is exact), and the |.| rides on the FMUL
+	// as an operand modifier: one instruction less than max/min/sub.
 	const float mx = fmaxf(a, b);
-	const float mn = fminf(a, b);
-	const float d = mx - mn;
-	const float p = fminf(d * 1000.0f, 15999.0f);
+	const float p = fminf(fabsf(a - b) * 1000.0f, 15999.0f);
 	const uint32_t bits = __float_as_uint(__fadd_rz(p, 8388608.0f));
 	float t;
 	asm("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(tab + (bits << 2)));
@@ -157,15 +157,44 @@ struct SeqUp {  // positions pos, pos+1, ...
 };
 
 // ------------------------------------------------------------------------------------------
-// backward, one segment (all HMMs f, all positions i).  barcode_hmm.c:3496-3607
-// The silent-state values of the next iteration (cs_arr[i-1], ps_arr[i-1]) are loaded one
-// position ahead: they come from L2/HBM and would otherwise stall the ordered chain.
+// Column parameters.  KIND 0: runtime live masks, values from the column record in shared memory.
+// KIND 1 ("STDU"): the standard column pattern (std_live) AND every HMM of the segment carries the
+// same five transition scalars the reference's set_hmm_transition_parameters() writes for it
+// (barcode_hmm.c:1787-1880) -- verified bit for bit by the host (tdg_host.cu: derive_model):
+//   MM = a (cols 0..n-2)          MI = b (cols 0..n-3), b2 (col n-2)      MD = b (cols 0..n-3)
+//   II = c, IM = d (cols 0..n-2)  DD = c, DM = d (cols 1..n-3)            DM(col n-2) = +0, MSKIP(col n-1) = +0
+// Then the values are registers / literal zeros and no parameter load remains in the inner loop.
 // ------------------------------------------------------------------------------------------
-template <int NC, bool STD, bool STORE>
+template <int KIND>
+__device__ __forceinline__ float trv(const float* r, const SegInfo& sg, int nc, int g, int field)
+{
+	if (KIND == 1) {
+		switch (field) {
+			case F_MM: return sg.ta;
+			case F_MI: return g == nc - 2 ? sg.tb2 : sg.tb;
+			case F_MD: return sg.tb;
+			case F_II: return sg.tc;
+			case F_IM: return sg.td;
+			case F_DD: return sg.tc;
+			case F_DM: return g == nc - 2 ? 0.0f : sg.td;
+			default: return 0.0f;  // MSKIP of the last column (the only other live transition)
+		}
+	}
+	return r[field];
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, one segment (all HMMs f, all positions i).  barcode_hmm.c:3496-3607
+// The silent-state values of the next iteration (cs[i-1], ps[i-1]) are loaded one position
+// ahead (+ an L1 prefetch kPrefetchDist ahead): they come from L2/HBM and would otherwise
+// stall the ordered chain.  Scratch layout of one HMM: [position][column][512 lanes] float2.
+// ------------------------------------------------------------------------------------------
+template <int NC, int KIND, bool STORE>
 __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, int x_term, bool last_seg,
                                             float2* __restrict__ bw, float* __restrict__ sb)
 {
+	constexpr bool STD = KIND == 1;
 	constexpr int N = Cols<NC, STD>::N;
 	constexpr int UN = NC > 0 ? N : 1;
 	const int nc = NC > 0 ? NC : sg.nc;
@@ -179,54 +208,64 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 		const int c0 = sg.colbase + f * nc;
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
 		const float* em = sm.emit + (size_t)c0 * kEmitRec;
-		float M[N], I[N], eMc[N], eIc[N];
+		float M[N], I[N], eMc[N];
+		float eIc[STD ? 1 : N];  // STDU: insert emissions are the same for every column of the segment
 		// state at i = len+1 : all -inf (:3466-3485); emissions of seqa[len+1] = a[len] (:3516)
 #pragma unroll UN
 		for (int g = 0; g < N; ++g) {
 			if (g < nc) {
 				M[g] = NEG_INF; I[g] = NEG_INF;
 				eMc[g] = em[g * kEmitRec + x_term];
-				eIc[g] = em[g * kEmitRec + 5 + x_term];
+				if (!STD) eIc[g] = em[g * kEmitRec + 5 + x_term];
 			}
 		}
+		if (STD) eIc[0] = em[5 + x_term];
+		const float sM0 = STD ? rec[F_SM] : 0.0f;
 		float ps1 = last_seg ? 0.0f : ps_arr[(size_t)(len + 1) * kBlock];
 		SeqDown sd;
 		sd.init(rd, off + lw - 1);
-		float cs_n = cs_arr[(size_t)lw * kBlock];
-		float ps_n = last_seg ? NEG_INF : ps_arr[(size_t)lw * kBlock];
+		float* csp = cs_arr + (size_t)lw * kBlock;          // -> cs[i]
+		const float* psp = ps_arr + (size_t)lw * kBlock;    // -> ps[i]
+		float2* bwp = bw + ((size_t)c0 * a.lmax + (size_t)(lw - 1) * nc) * kBlock;  // -> (position i, column 0)
+		float cs_n = *csp;
+		float ps_n = last_seg ? NEG_INF : *psp;
 		for (int i = lw; i >= 1; --i) {
 			const int x0 = sd.get();  // seqa[i]
 			float cs = cs_n;
 			const float ps0 = ps_n;
-			cs_n = cs_arr[(size_t)(i - 1) * kBlock];
-			if (!last_seg) ps_n = ps_arr[(size_t)(i - 1) * kBlock];
+			cs_n = *(csp - kBlock);
+			if (!last_seg) ps_n = *(psp - kBlock);
 			if (i > kPrefetchDist) {  // pull the silent-state lines of iteration i-kPrefetchDist towards L1
-				prefetch_l1(&cs_arr[(size_t)(i - kPrefetchDist) * kBlock]);
-				if (!last_seg) prefetch_l1(&ps_arr[(size_t)(i - kPrefetchDist) * kBlock]);
+				prefetch_l1(csp - (size_t)kPrefetchDist * kBlock);
+				if (!last_seg) prefetch_l1(psp - (size_t)kPrefetchDist * kBlock);
 			}
 			if (i <= len) {
-				float eM0[N], eI0[N];
+				float eM0[N];
+				float eI0[STD ? 1 : N];
 #pragma unroll UN
 				for (int g = 0; g < N; ++g) {
 					if (g < nc) {
 						eM0[g] = em[g * kEmitRec + x0];
-						eI0[g] = em[g * kEmitRec + 5 + x0];
+						if (!STD) eI0[g] = em[g * kEmitRec + 5 + x0];
 					}
 				}
+				if (STD) eI0[0] = em[5 + x0];
+#define EIC(g) eIc[STD ? 0 : (g)]
+#define EI0(g) eI0[STD ? 0 : (g)]
 				// ---- last column (:3518-3541)
 				float oldMp, newMp, D;
 				{
 					const float* r = rec + m * kColRec;
 					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
-					float nM = live_of<STD>(nc, m, F_MSKIP, lv) ? ps1 + r[F_MSKIP] : NEG_INF;
+					float nM = live_of<STD>(nc, m, F_MSKIP, lv) ? ps1 + trv<KIND>(r, sg, nc, m, F_MSKIP) : NEG_INF;
 					float nI = live_of<STD>(nc, m, F_ISKIP, lv) ? ps1 + r[F_ISKIP] : NEG_INF;
 					if (live_of<STD>(nc, m, F_IM, lv)) nI = LS(nI, M[m] + r[F_IM] + eMc[m], tab);
-					if (live_of<STD>(nc, m, F_II, lv)) nI = LS(nI, I[m] + r[F_II] + eIc[m], tab);
+					if (live_of<STD>(nc, m, F_II, lv)) nI = LS(nI, I[m] + r[F_II] + EIC(m), tab);
 					if (live_of<STD>(nc, m, F_SM, lv)) cs = LS(cs, nM + r[F_SM] + eM0[m], tab);
-					if (live_of<STD>(nc, m, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + eI0[m], tab);
+					if (live_of<STD>(nc, m, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + EI0(m), tab);
 					oldMp = M[m]; newMp = nM; D = NEG_INF;
 					M[m] = nM; I[m] = nI;
-					if (STORE) __stcs(&bw[((size_t)(c0 + m) * a.lmax + (i - 1)) * kBlock], make_float2(nM, nI));
+					if (STORE) __stcs(&bwp[(size_t)m * kBlock], make_float2(nM, nI));
 				}
 				// ---- columns m-1 .. 0 (:3545-3589)
 #pragma unroll UN
@@ -239,43 +278,47 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 						const float oldMg = M[g];
 						float v;
 						// M_backward[g][i]
-						v = live_of<STD>(nc, g, F_MM, lv) ? oldMp + eMc[p] + r[F_MM] : NEG_INF;
+						v = live_of<STD>(nc, g, F_MM, lv) ? oldMp + eMc[p] + trv<KIND>(r, sg, nc, g, F_MM) : NEG_INF;
 						if (live_of<STD>(nc, g, F_MSKIP, lv)) v = LS(v, ps1 + r[F_MSKIP], tab);
-						if (live_of<STD>(nc, g, F_MI, lv)) v = LS(v, I[g] + eIc[g] + r[F_MI], tab);
-						if (live_of<STD>(nc, g, F_MD, lv)) v = LS(v, D + r[F_MD], tab);
+						if (live_of<STD>(nc, g, F_MI, lv)) v = LS(v, I[g] + EIC(g) + trv<KIND>(r, sg, nc, g, F_MI), tab);
+						if (live_of<STD>(nc, g, F_MD, lv)) v = LS(v, D + trv<KIND>(r, sg, nc, g, F_MD), tab);
 						const float nM = v;
 						// I_backward[g][i]
-						v = live_of<STD>(nc, g, F_II, lv) ? I[g] + r[F_II] + eIc[g] : NEG_INF;
+						v = live_of<STD>(nc, g, F_II, lv) ? I[g] + trv<KIND>(r, sg, nc, g, F_II) + EIC(g) : NEG_INF;
 						if (live_of<STD>(nc, g, F_ISKIP, lv)) v = LS(v, ps1 + r[F_ISKIP], tab);
-						if (live_of<STD>(nc, g, F_IM, lv)) v = LS(v, oldMp + r[F_IM] + eMc[p], tab);
+						if (live_of<STD>(nc, g, F_IM, lv)) v = LS(v, oldMp + trv<KIND>(r, sg, nc, g, F_IM) + eMc[p], tab);
 						const float nI = v;
 						// D_backward[g][i]
 						{
 							const bool ldd = live_of<STD>(nc, g, F_DD, lv);
 							const bool ldm = live_of<STD>(nc, g, F_DM, lv);
 							float dv = NEG_INF;
-							if (ldd) dv = D + r[F_DD];
+							if (ldd) dv = D + trv<KIND>(r, sg, nc, g, F_DD);
 							if (ldm) {
-								const float t = newMp + eM0[p] + r[F_DM];
+								const float t = newMp + eM0[p] + trv<KIND>(r, sg, nc, g, F_DM);
 								dv = ldd ? LS(dv, t, tab) : t;
 							}
 							D = dv;
 						}
-						if (live_of<STD>(nc, g, F_SM, lv)) cs = LS(cs, nM + r[F_SM] + eM0[g], tab);
-						if (live_of<STD>(nc, g, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + eI0[g], tab);
+						if (live_of<STD>(nc, g, F_SM, lv)) cs = LS(cs, nM + (STD ? sM0 : r[F_SM]) + eM0[g], tab);
+						if (live_of<STD>(nc, g, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + EI0(g), tab);
 						M[g] = nM; I[g] = nI;
 						oldMp = oldMg; newMp = nM;
-						if (STORE) __stcs(&bw[((size_t)(c0 + g) * a.lmax + (i - 1)) * kBlock], make_float2(nM, nI));
+						if (STORE) __stcs(&bwp[(size_t)g * kBlock], make_float2(nM, nI));
 					}
 				}
 				if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // once per HMM f (:3604)
-				cs_arr[(size_t)i * kBlock] = cs;
+				*csp = cs;
 #pragma unroll UN
 				for (int g = 0; g < N; ++g) {
-					if (g < nc) { eMc[g] = eM0[g]; eIc[g] = eI0[g]; }
+					if (g < nc) { eMc[g] = eM0[g]; if (!STD) eIc[g] = eI0[g]; }
 				}
+				if (STD) eIc[0] = eI0[0];
 				ps1 = ps0;
+#undef EIC
+#undef EI0
 			}
+			csp -= kBlock; psp -= kBlock; bwp -= (size_t)nc * kBlock;
 		}
 	}
 }
@@ -317,22 +360,28 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 		const bool last = (j == a.S - 1);
 		const int kind = sg.kind;  // host-selected code path: 0 generic, 1 STD
 		const int nc = sg.nc;
-#define BWD_CASE(NCV, STDV) bwd_segment<NCV, STDV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb)
+#define BWD_CASE(NCV, KINDV) bwd_segment<NCV, KINDV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb)
 		if (kind == 1) {
 			switch (nc) {
-				case 3: BWD_CASE(3, true); break;
-				case 4: BWD_CASE(4, true); break;
-				case 5: BWD_CASE(5, true); break;
-				case 6: BWD_CASE(6, true); break;
-				case 7: BWD_CASE(7, true); break;
-				case 8: BWD_CASE(8, true); break;
-				default: BWD_CASE(0, false); break;
+				case 3: BWD_CASE(3, 1); break;
+				case 4: BWD_CASE(4, 1); break;
+				case 5: BWD_CASE(5, 1); break;
+				case 6: BWD_CASE(6, 1); break;
+				case 7: BWD_CASE(7, 1); break;
+				case 8: BWD_CASE(8, 1); break;
+				default: BWD_CASE(0, 0); break;
 			}
 		} else {
 			switch (nc) {
-				case 1: BWD_CASE(1, false); break;
-				case 2: BWD_CASE(2, false); break;
-				default: BWD_CASE(0, false); break;
+				case 1: BWD_CASE(1, 0); break;
+				case 2: BWD_CASE(2, 0); break;
+				case 3: BWD_CASE(3, 0); break;
+				case 4: BWD_CASE(4, 0); break;
+				case 5: BWD_CASE(5, 0); break;
+				case 6: BWD_CASE(6, 0); break;
+				case 7: BWD_CASE(7, 0); break;
+				case 8: BWD_CASE(8, 0); break;
+				default: BWD_CASE(0, 0); break;
 			}
 		}
 #undef BWD_CASE
@@ -342,15 +391,16 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 
 // ------------------------------------------------------------------------------------------
 // forward + posterior, one segment.  barcode_hmm.c:4199-4345
-// Mb/Ib of position i+1 (HBM), cs_arr[i+1] and ps_arr[i+1] are loaded one position ahead.
+// Mb/Ib of position i+1 (HBM), cs[i+1] and ps[i+1] are loaded one position ahead.
 // ------------------------------------------------------------------------------------------
-template <int NC, bool STD>
+template <int NC, int KIND>
 __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, float B,
                                             const float2* __restrict__ bw, float* __restrict__ sf,
                                             float* __restrict__ post, float* __restrict__ tp,
                                             uint32_t* __restrict__ prange)
 {
+	constexpr bool STD = KIND == 1;
 	constexpr int N = Cols<NC, STD>::N;
 	constexpr int UN = NC > 0 ? N : 1;
 	constexpr int NB = NC > 0 ? NC : 1;  // prefetch registers only on the unrolled paths
@@ -361,13 +411,14 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 	const TabAddr tab = sm.tab;
 	const bool first_seg = (j == 0);
 	const int skip_live = sg.skip_live;
+	const size_t bstep = (size_t)nc * kBlock;
 
 	for (int f = 0; f < sg.nh; ++f) {
 		const int h = sg.hmmbase + f;
 		const int c0 = sg.colbase + f * nc;
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
 		const float* em = sm.emit + (size_t)c0 * kEmitRec;
-		const float2* bwc = bw + (size_t)c0 * a.lmax * kBlock;
+		const float2* bwq = bw + (size_t)c0 * a.lmax * kBlock;  // -> (position 1, column 0); walks ahead of i
 		float M[N], I[N];
 		float2 bn[NB];
 #pragma unroll UN
@@ -376,39 +427,44 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 		}
 		if (NC > 0) {
 #pragma unroll
-			for (int g = 0; g < NB; ++g) bn[g] = __ldcs(&bwc[((size_t)g * a.lmax) * kBlock]);
+			for (int g = 0; g < NB; ++g) bn[g] = __ldcs(&bwq[(size_t)g * kBlock]);
 		}
+		const float sM0 = STD ? rec[F_SM] : 0.0f;
 		float TP = NEG_INF;
 		int pfirst = 0xFFFF, plast = 0;  // positions whose posterior is >= -104 (exp != 0), for k_label
 		float ps1 = first_seg ? 0.0f : ps_arr[0];  // psilent[0]
 		SeqUp su;
 		su.init(rd, off, a.words);
-		float cs_n = cs_arr[(size_t)1 * kBlock];
-		float ps_n = first_seg ? NEG_INF : ps_arr[(size_t)1 * kBlock];
+		float* csp = cs_arr + kBlock;         // -> cs[i]
+		const float* psp = ps_arr + kBlock;   // -> ps[i]
+		float* pp = post + (size_t)h * kBlock;  // -> posterior (position i, hmm h)
+		float cs_n = *csp;
+		float ps_n = first_seg ? NEG_INF : *psp;
 		for (int i = 1; i <= lw; ++i) {
 			const int x = su.get();  // seqa[i]
 			float cs = cs_n;
 			const float ps0 = ps_n;
 			float2 bc[NB];
 			if (NC > 0) {
-				const int ip = (i < a.lmax) ? i : a.lmax - 1;  // position i+1, clamped to the scratch
+				if (i < a.lmax) bwq += bstep;  // position i+1, clamped to the scratch
 #pragma unroll
-				for (int g = 0; g < NB; ++g) { bc[g] = bn[g]; bn[g] = __ldcs(&bwc[((size_t)g * a.lmax + ip) * kBlock]); }
+				for (int g = 0; g < NB; ++g) { bc[g] = bn[g]; bn[g] = __ldcs(&bwq[(size_t)g * kBlock]); }
 			}
-			cs_n = cs_arr[(size_t)(i + 1) * kBlock];
-			if (!first_seg) ps_n = ps_arr[(size_t)(i + 1) * kBlock];
+			cs_n = *(csp + kBlock);
+			if (!first_seg) ps_n = *(psp + kBlock);
 			if (i <= len) {
 				float P;
 				float oldMp, oldIp, newMp, D;
+				const float eIu = STD ? em[5 + x] : 0.0f;  // STDU: one insert emission per position
 				// ---- column 0 (:4218-4266)
 				{
 					const float* r = rec;
 					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
-					const float2 b = NC > 0 ? bc[0] : __ldcs(&bwc[(size_t)(i - 1) * kBlock]);
-					const float eM = em[x], eI = em[5 + x];
+					const float2 b = NC > 0 ? bc[0] : __ldcs(&bwq[((size_t)(i - 1) * nc) * kBlock]);
+					const float eM = em[x], eI = STD ? eIu : em[5 + x];
 					const bool lsm = live_of<STD>(nc, 0, F_SM, lv);
 					const bool lsi = live_of<STD>(nc, 0, F_SI, lv);
-					const float nM = lsm ? ps1 + r[F_SM] + eM : NEG_INF;
+					const float nM = lsm ? ps1 + (STD ? sM0 : r[F_SM]) + eM : NEG_INF;
 					const float tM = nM + b.x - B;
 					TP = LS(TP, tM, tab);
 					P = tM;  // logsum(-inf, tM) == tM
@@ -416,8 +472,8 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 					bool have = false;
 					v = NEG_INF;
 					if (lsi) { v = ps1 + r[F_SI]; have = true; }
-					if (live_of<STD>(nc, 0, F_II, lv)) { const float t = I[0] + r[F_II]; v = have ? LS(v, t, tab) : t; have = true; }
-					if (live_of<STD>(nc, 0, F_MI, lv)) { const float t = M[0] + r[F_MI]; v = have ? LS(v, t, tab) : t; have = true; }
+					if (live_of<STD>(nc, 0, F_II, lv)) { const float t = I[0] + trv<KIND>(r, sg, nc, 0, F_II); v = have ? LS(v, t, tab) : t; have = true; }
+					if (live_of<STD>(nc, 0, F_MI, lv)) { const float t = M[0] + trv<KIND>(r, sg, nc, 0, F_MI); v = have ? LS(v, t, tab) : t; have = true; }
 					const float nI = v + eI;
 					if (lsi) TP = LS(TP, ps1 + r[F_SI] + eI + b.y - B, tab);
 					P = LS(P, nI + b.y - B, tab);
@@ -435,45 +491,46 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 						const float* rp = rec + p * kColRec;
 						const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
 						const uint32_t lp = STD ? 0u : __float_as_uint(rp[F_LIVE]);
-						const float2 b = NC > 0 ? bc[NC > 0 ? g : 0] : __ldcs(&bwc[((size_t)g * a.lmax + (i - 1)) * kBlock]);
-						const float eM = em[g * kEmitRec + x], eI = em[g * kEmitRec + 5 + x];
+						const float2 b = NC > 0 ? bc[NC > 0 ? g : 0] : __ldcs(&bwq[((size_t)(i - 1) * nc + g) * kBlock]);
+						const float eM = em[g * kEmitRec + x], eI = STD ? eIu : em[g * kEmitRec + 5 + x];
 						const float oldMg = M[g], oldIg = I[g];
 						float v; bool have;
 						// M_forward[g][i]
 						v = NEG_INF; have = false;
 						if (live_of<STD>(nc, g, F_SM, lv)) { v = ps1 + r[F_SM]; have = true; }
-						if (live_of<STD>(nc, p, F_MM, lp)) { const float t = oldMp + rp[F_MM]; v = have ? LS(v, t, tab) : t; have = true; }
-						if (live_of<STD>(nc, p, F_IM, lp)) { const float t = oldIp + rp[F_IM]; v = have ? LS(v, t, tab) : t; have = true; }
-						if (live_of<STD>(nc, p, F_DM, lp)) { const float t = D + rp[F_DM]; v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, p, F_MM, lp)) { const float t = oldMp + trv<KIND>(rp, sg, nc, p, F_MM); v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, p, F_IM, lp)) { const float t = oldIp + trv<KIND>(rp, sg, nc, p, F_IM); v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, p, F_DM, lp)) { const float t = D + trv<KIND>(rp, sg, nc, p, F_DM); v = have ? LS(v, t, tab) : t; have = true; }
 						const float nM = v + eM;
 						const bool m_reach = STD ? true : have;
 						if (m_reach) P = LS(P, nM + b.x - B, tab);
 						// I_forward[g][i]
 						v = NEG_INF; have = false;
 						if (live_of<STD>(nc, g, F_SI, lv)) { v = ps1 + r[F_SI]; have = true; }
-						if (live_of<STD>(nc, g, F_II, lv)) { const float t = oldIg + r[F_II]; v = have ? LS(v, t, tab) : t; have = true; }
-						if (live_of<STD>(nc, g, F_MI, lv)) { const float t = oldMg + r[F_MI]; v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, g, F_II, lv)) { const float t = oldIg + trv<KIND>(r, sg, nc, g, F_II); v = have ? LS(v, t, tab) : t; have = true; }
+						if (live_of<STD>(nc, g, F_MI, lv)) { const float t = oldMg + trv<KIND>(r, sg, nc, g, F_MI); v = have ? LS(v, t, tab) : t; have = true; }
 						const float nI = v + eI;
 						if (have) P = LS(P, nI + b.y - B, tab);
 						// D_forward[g][i]
 						{
 							float dv = NEG_INF; bool dh = false;
-							if (live_of<STD>(nc, p, F_MD, lp)) { dv = newMp + rp[F_MD]; dh = true; }
-							if (live_of<STD>(nc, p, F_DD, lp)) { const float t = D + rp[F_DD]; dv = dh ? LS(dv, t, tab) : t; }
+							if (live_of<STD>(nc, p, F_MD, lp)) { dv = newMp + trv<KIND>(rp, sg, nc, p, F_MD); dh = true; }
+							if (live_of<STD>(nc, p, F_DD, lp)) { const float t = D + trv<KIND>(rp, sg, nc, p, F_DD); dv = dh ? LS(dv, t, tab) : t; }
 							D = dv;
 						}
-						if (live_of<STD>(nc, g, F_MSKIP, lv)) cs = LS(cs, nM + r[F_MSKIP], tab);
+						if (live_of<STD>(nc, g, F_MSKIP, lv)) cs = LS(cs, nM + trv<KIND>(r, sg, nc, g, F_MSKIP), tab);
 						if (live_of<STD>(nc, g, F_ISKIP, lv)) cs = LS(cs, nI + r[F_ISKIP], tab);
 						oldMp = oldMg; oldIp = oldIg; newMp = nM;
 						M[g] = nM; I[g] = nI;
 					}
 				}
 				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
-				cs_arr[(size_t)i * kBlock] = cs;
-				__stcs(&post[((size_t)(i - 1) * a.H + h) * kBlock], P);
+				*csp = cs;
+				__stcs(pp, P);
 				if (!(P < -104.0f)) { plast = i; pfirst = min(pfirst, i); }
 				ps1 = ps0;
 			}
+			csp += kBlock; psp += kBlock; pp += (size_t)a.H * kBlock;
 		}
 		tp[(size_t)h * kBlock] = TP;
 		prange[(size_t)h * kBlock] = ((uint32_t)plast << 16) | (uint32_t)pfirst;
@@ -524,22 +581,28 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 		const SegInfo sg = a.seg[j];
 		const int kind = sg.kind;
 		const int nc = sg.nc;
-#define FWD_CASE(NCV, STDV) fwd_segment<NCV, STDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sf, post, tp, prange)
+#define FWD_CASE(NCV, KINDV) fwd_segment<NCV, KINDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sf, post, tp, prange)
 		if (kind == 1) {
 			switch (nc) {
-				case 3: FWD_CASE(3, true); break;
-				case 4: FWD_CASE(4, true); break;
-				case 5: FWD_CASE(5, true); break;
-				case 6: FWD_CASE(6, true); break;
-				case 7: FWD_CASE(7, true); break;
-				case 8: FWD_CASE(8, true); break;
-				default: FWD_CASE(0, false); break;
+				case 3: FWD_CASE(3, 1); break;
+				case 4: FWD_CASE(4, 1); break;
+				case 5: FWD_CASE(5, 1); break;
+				case 6: FWD_CASE(6, 1); break;
+				case 7: FWD_CASE(7, 1); break;
+				case 8: FWD_CASE(8, 1); break;
+				default: FWD_CASE(0, 0); break;
 			}
 		} else {
 			switch (nc) {
-				case 1: FWD_CASE(1, false); break;
-				case 2: FWD_CASE(2, false); break;
-				default: FWD_CASE(0, false); break;
+				case 1: FWD_CASE(1, 0); break;
+				case 2: FWD_CASE(2, 0); break;
+				case 3: FWD_CASE(3, 0); break;
+				case 4: FWD_CASE(4, 0); break;
+				case 5: FWD_CASE(5, 0); break;
+				case 6: FWD_CASE(6, 0); break;
+				case 7: FWD_CASE(7, 0); break;
+				case 8: FWD_CASE(8, 0); break;
+				default: FWD_CASE(0, 0); break;
 			}
 		}
 #undef FWD_CASE
