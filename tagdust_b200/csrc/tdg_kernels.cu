@@ -199,6 +199,9 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 	constexpr int UN = NC > 0 ? N : 1;
 	const int nc = NC > 0 ? NC : sg.nc;
 	const int m = nc - 1;
+	// STDU: the last column is not stored -- Mb[m][i] = ps[i+1] + 0 and Ib[m][i] = -inf (std_live);
+	// k_forward rebuilds it from silent_backward of the next segment.
+	const int ncs = STD ? nc - 1 : nc;
 	const size_t W = (size_t)(a.lmax + 2);
 	float* cs_arr = sb + ((size_t)j * W) * kBlock;
 	const float* ps_arr = sb + ((size_t)(j + 1) * W) * kBlock;
@@ -226,7 +229,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 		sd.init(rd, off + lw - 1);
 		float* csp = cs_arr + (size_t)lw * kBlock;          // -> cs[i]
 		const float* psp = ps_arr + (size_t)lw * kBlock;    // -> ps[i]
-		float2* bwp = bw + ((size_t)c0 * a.lmax + (size_t)(lw - 1) * nc) * kBlock;  // -> (position i, column 0)
+		float2* bwp = bw + ((size_t)c0 * a.lmax + (size_t)(lw - 1) * ncs) * kBlock;  // -> (position i, column 0)
 		float cs_n = *csp;
 		float ps_n = last_seg ? NEG_INF : *psp;
 		for (int i = lw; i >= 1; --i) {
@@ -265,7 +268,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 					if (live_of<STD>(nc, m, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + EI0(m), tab);
 					oldMp = M[m]; newMp = nM; D = NEG_INF;
 					M[m] = nM; I[m] = nI;
-					if (STORE) __stcs(&bwp[(size_t)m * kBlock], make_float2(nM, nI));
+					if (STORE && !STD) __stcs(&bwp[(size_t)m * kBlock], make_float2(nM, nI));
 				}
 				// ---- columns m-1 .. 0 (:3545-3589)
 #pragma unroll UN
@@ -318,7 +321,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 #undef EIC
 #undef EI0
 			}
-			csp -= kBlock; psp -= kBlock; bwp -= (size_t)nc * kBlock;
+			csp -= kBlock; psp -= kBlock; bwp -= (size_t)ncs * kBlock;
 		}
 	}
 }
@@ -396,22 +399,24 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 template <int NC, int KIND>
 __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, float B,
-                                            const float2* __restrict__ bw, float* __restrict__ sf,
-                                            float* __restrict__ post, float* __restrict__ tp,
+                                            const float2* __restrict__ bw, const float* __restrict__ sbk,
+                                            float* __restrict__ sf, float* __restrict__ post, float* __restrict__ tp,
                                             uint32_t* __restrict__ prange)
 {
 	constexpr bool STD = KIND == 1;
 	constexpr int N = Cols<NC, STD>::N;
 	constexpr int UN = NC > 0 ? N : 1;
-	constexpr int NB = NC > 0 ? NC : 1;  // prefetch registers only on the unrolled paths
+	constexpr int NB = NC > 0 ? (STD ? NC - 1 : NC) : 1;  // prefetch registers only on the unrolled paths
 	const int nc = NC > 0 ? NC : sg.nc;
+	const int ncs = STD ? nc - 1 : nc;  // stored columns (k_backward does not store the last STDU column)
+	const bool last_seg = (j == a.S - 1);
 	const size_t W = (size_t)(a.lmax + 2);
 	float* cs_arr = sf + ((size_t)j * W) * kBlock;
 	const float* ps_arr = sf + ((size_t)(j - 1) * W) * kBlock;  // only dereferenced when j > 0
 	const TabAddr tab = sm.tab;
 	const bool first_seg = (j == 0);
 	const int skip_live = sg.skip_live;
-	const size_t bstep = (size_t)nc * kBlock;
+	const size_t bstep = (size_t)ncs * kBlock;
 
 	for (int f = 0; f < sg.nh; ++f) {
 		const int h = sg.hmmbase + f;
@@ -440,10 +445,19 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 		float* pp = post + (size_t)h * kBlock;  // -> posterior (position i, hmm h)
 		float cs_n = *csp;
 		float ps_n = first_seg ? NEG_INF : *psp;
+		// STDU: silent_backward of the next segment at position i+1 (= Mb of the unstored last column)
+		const float* qb = sbk + ((size_t)(j + 1) * W + 2) * kBlock;
+		float q_n = (STD && !last_seg) ? *qb : NEG_INF;
 		for (int i = 1; i <= lw; ++i) {
 			const int x = su.get();  // seqa[i]
 			float cs = cs_n;
 			const float ps0 = ps_n;
+			float q0 = NEG_INF;
+			if (STD) {
+				q0 = last_seg ? (i == len ? 0.0f : NEG_INF) : q_n;
+				qb += kBlock;
+				if (!last_seg && i < lw) q_n = *qb;
+			}
 			float2 bc[NB];
 			if (NC > 0) {
 				if (i < a.lmax) bwq += bstep;  // position i+1, clamped to the scratch
@@ -491,7 +505,9 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 						const float* rp = rec + p * kColRec;
 						const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
 						const uint32_t lp = STD ? 0u : __float_as_uint(rp[F_LIVE]);
-						const float2 b = NC > 0 ? bc[NC > 0 ? g : 0] : __ldcs(&bwq[((size_t)(i - 1) * nc + g) * kBlock]);
+						float2 b;
+						if (STD && g == NC - 1) b = make_float2(q0 + trv<KIND>(r, sg, nc, g, F_MSKIP), NEG_INF);  // as k_backward computes it
+						else b = NC > 0 ? bc[(NC > 0 && !(STD && g == NC - 1)) ? g : 0] : __ldcs(&bwq[((size_t)(i - 1) * nc + g) * kBlock]);
 						const float eM = em[g * kEmitRec + x], eI = STD ? eIu : em[g * kEmitRec + 5 + x];
 						const float oldMg = M[g], oldIg = I[g];
 						float v; bool have;
@@ -560,6 +576,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 	const SeqReader rd = make_reader(a, valid ? read : 0);
 	const size_t W = (size_t)(a.lmax + 2);
 	const float2* bw = a.bw + (size_t)blockIdx.x * ((size_t)a.C * a.lmax) * kBlock + threadIdx.x;
+	const float* sbk = a.sb + (size_t)blockIdx.x * ((size_t)a.S * W) * kBlock + threadIdx.x;
 	float* sf = a.sf + (size_t)blockIdx.x * ((size_t)a.S * W) * kBlock + threadIdx.x;
 	float* post = a.post + (size_t)blockIdx.x * ((size_t)a.lmax * a.H) * kBlock + threadIdx.x;
 	float* tp = a.tp + (size_t)blockIdx.x * ((size_t)a.H) * kBlock + threadIdx.x;
@@ -581,7 +598,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 		const SegInfo sg = a.seg[j];
 		const int kind = sg.kind;
 		const int nc = sg.nc;
-#define FWD_CASE(NCV, KINDV) fwd_segment<NCV, KINDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sf, post, tp, prange)
+#define FWD_CASE(NCV, KINDV) fwd_segment<NCV, KINDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sbk, sf, post, tp, prange)
 		if (kind == 1) {
 			switch (nc) {
 				case 3: FWD_CASE(3, 1); break;
