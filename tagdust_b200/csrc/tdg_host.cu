@@ -409,7 +409,7 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 	m->dev.resize(ctx->devs.size());
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
 		DeviceCtx& d = ctx->devs[k];
-		if (smem > d.smem_optin) {
+		if (smem + 64 > d.smem_optin) {  // + the kernels' few bytes of static shared memory
 			tdg_model_destroy(m);
 			return fail(TDG_EINVAL, "architecture too large for shared memory: needs %zu B, device allows %zu B", smem, d.smem_optin);
 		}

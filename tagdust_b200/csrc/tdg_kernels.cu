@@ -83,9 +83,14 @@ __device__ __forceinline__ Smem stage_smem(const KArgs& a, float* smem)
 	for (int k = threadIdx.x; k < kLogsumSize; k += blockDim.x) smem[k] = a.logsum_tab[k];
 	float* m = smem + kLogsumSize;
 	for (int k = threadIdx.x; k < a.model_floats; k += blockDim.x) m[k] = a.model_blob[k];
+	// The pre-offset table base is bounced through shared memory so that it reaches the inner
+	// loops as an opaque register: ptxas otherwise re-splits it into (window base, constant) and
+	// spends a second integer add per logsum on the constant.
+	__shared__ volatile uint32_t s_tab_addr;
+	if (threadIdx.x == 0) s_tab_addr = make_tab_addr(smem);
 	__syncthreads();
 	Smem s;
-	s.tab = make_tab_addr(smem);
+	s.tab = s_tab_addr;
 	s.colrec = m;
 	s.emit = m + (size_t)a.C * kColRec;
 	return s;
@@ -902,17 +907,26 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 // ------------------------------------------------------------------------------------------
 size_t decode_smem_bytes(int model_floats) { return (size_t)(kLogsumSize + model_floats) * sizeof(float); }
 
+// smem_bytes = the device's opt-in maximum per block; each kernel's own static shared memory
+// is subtracted so that the dynamic limit requested is the largest the driver accepts.
+template <class K>
+static int set_dyn_smem(K kernel, int smem_bytes, int cap)
+{
+	cudaFuncAttributes fa;
+	cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+	if (e != cudaSuccess) return (int)e;
+	int dyn = smem_bytes - (int)fa.sharedSizeBytes;
+	if (cap > 0 && dyn > cap) dyn = cap;
+	return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+}
+
 int kernels_configure(int smem_bytes)
 {
-	cudaError_t e;
-	e = cudaFuncSetAttribute(k_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-	if (e != cudaSuccess) return (int)e;
-	e = cudaFuncSetAttribute(k_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-	if (e != cudaSuccess) return (int)e;
-	e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-	if (e != cudaSuccess) return (int)e;
-	e = cudaFuncSetAttribute(k_label, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	if (e != cudaSuccess) return (int)e;
+	int e;
+	if ((e = set_dyn_smem(k_backward<true>, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_backward<false>, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_forward, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_label, smem_bytes, 110 * 1024))) return e;
 	return 0;
 }
 
