@@ -547,8 +547,10 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				}
 				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
 				*csp = cs;
-				__stcs(pp, P);
+				// k_label's structured DP only reads posteriors inside [pfirst, plast] (below -104 exp()
+				// is exactly 0), so nothing is stored before the first position of that window
 				if (!(P < -104.0f)) { plast = i; pfirst = min(pfirst, i); }
+				if (pfirst != 0xFFFF || !a.dp_structured) __stcs(pp, P);
 				ps1 = ps0;
 			}
 			csp += kBlock; psp += kBlock; pp += (size_t)a.H * kBlock;
@@ -704,9 +706,23 @@ __device__ __forceinline__ float post_exp(float x)
 __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 {
 	__shared__ int s_src[TDG_MAX_HMMS_DEV * kMaxSources];
-	extern __shared__ float dsm[];  // structured path: D row [H][blockDim] floats, then posterior ranges [H][blockDim] u32
+	__shared__ uint8_t s_segflag[kMaxSegments];  // bit 0: no HMM of the segment has a predecessor but itself; bit 1: all share one source list
+	extern __shared__ float dsm[];  // structured path: D row [H][bs] floats, posterior ranges [H][bs] u32
 	const int bs = blockDim.x;
 	for (int k = threadIdx.x; k < a.H * kMaxSources; k += bs) s_src[k] = a.dp_src[k];
+	__syncthreads();
+	if ((int)threadIdx.x < a.S) {
+		const int hb = a.seg[threadIdx.x].hmmbase, nh = a.seg[threadIdx.x].nh;
+		bool self_only = true, uniform = true;
+		for (int f = 0; f < nh; ++f)
+			for (int q = 0; q < kMaxSources; ++q) {
+				const int src = s_src[(hb + f) * kMaxSources + q];
+				if (q == 0 && src != INT32_MIN) self_only = false;
+				if (src != s_src[hb * kMaxSources + q]) uniform = false;
+				if (src != INT32_MIN && src >= hb) uniform = false;  // a predecessor inside the segment is updated in place
+			}
+		s_segflag[threadIdx.x] = (self_only ? 1 : 0) | (uniform ? 2 : 0);
+	}
 	__syncthreads();
 	const int slot = blockIdx.x * bs + threadIdx.x;
 	const int read = slot;
@@ -730,12 +746,30 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 			// The DP row lives in shared memory and is updated in place from the highest HMM index
 			// down (every predecessor of j has a lower index, so it still holds row i-1).  Posterior
 			// entries outside [first,last] of their HMM (k_forward's prange) are < -104 and exp to
-			// exactly 0: they are neither loaded nor exponentiated.
+			// exactly 0: they are neither stored by k_forward nor loaded here.
+			//
+			// HMMs whose only predecessor is themselves (the first segment): D[i][j] = D[i-1][j] + p
+			// and path[i][j] = j, so outside their range nothing changes and no path byte is kept;
+			// positions outside the union of the segment's ranges skip the segment altogether.  All D
+			// entries are non-decreasing in i (p >= 0), so the segment's first-argmax is maintained
+			// incrementally: an entry that rises above the maximum, or ties it at a lower index, takes over.
 			constexpr int CH = 8;
 			float* D = dsm + threadIdx.x;
 			uint32_t* rng = (uint32_t*)(dsm + (size_t)H * bs) + threadIdx.x;
 			const uint32_t* prange = a.prange + (size_t)cta * H * kBlock + t;
-			for (int j = 0; j < H; ++j) { D[(size_t)j * bs] = 0.0f; rng[(size_t)j * bs] = prange[(size_t)j * kBlock]; }
+			int sfirst[kMaxSegments], slast[kMaxSegments];  // union of the posterior ranges of a segment's HMMs
+			for (int s = 0; s < a.S; ++s) {
+				const int hb = a.seg[s].hmmbase, nh = a.seg[s].nh;
+				int lo = 0xFFFF, hi = 0;
+				for (int f = 0; f < nh; ++f) {
+					const int j = hb + f;
+					const uint32_t r = prange[(size_t)j * kBlock];
+					D[(size_t)j * bs] = 0.0f;
+					rng[(size_t)j * bs] = r;
+					lo = min(lo, (int)(r & 0xFFFFu)); hi = max(hi, (int)(r >> 16));
+				}
+				sfirst[s] = lo; slast[s] = hi;
+			}
 			for (int i = 1; i <= len; ++i) {
 				const float* row = post + ((size_t)(i - 1) * H) * kBlock;
 				uint8_t* prow_path = path + ((size_t)(i - 1) * H) * kBlock;
@@ -743,6 +777,46 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 				int nsegarg[kMaxSegments];
 				for (int s = a.S - 1; s >= 0; --s) {
 					const int hb = a.seg[s].hmmbase, nh = a.seg[s].nh;
+					const int flag = s_segflag[s];
+					if (flag & 1) {
+						float cm = segmax[s]; int ca = segarg[s];
+						if (i >= sfirst[s] && i <= slast[s]) {
+							for (int f1 = 0; f1 < nh; f1 += CH) {
+								float pv[CH];
+#pragma unroll
+								for (int k = 0; k < CH; ++k) {
+									const int f = f1 + k;
+									if (f < nh) {
+										const uint32_t r = rng[(size_t)(hb + f) * bs];
+										pv[k] = (i >= (int)(r & 0xFFFFu) && i <= (int)(r >> 16)) ? __ldcs(&row[(size_t)(hb + f) * kBlock]) : NEG_INF;
+									}
+								}
+#pragma unroll
+								for (int k = 0; k < CH; ++k) {
+									const int f = f1 + k;
+									if (f < nh && pv[k] >= -104.0f) {
+										const int j = hb + f;
+										const float nd = post_exp(pv[k]) + D[(size_t)j * bs];
+										D[(size_t)j * bs] = nd;
+										if (nd > cm || (nd == cm && j < ca)) { cm = nd; ca = j; }
+									}
+								}
+							}
+						}
+						nsegmax[s] = cm; nsegarg[s] = ca;
+						continue;
+					}
+					float ubest = -1.0f; int uarg = -1;
+					if (flag & 2) {  // one source list for the whole segment: evaluate it once
+						for (int q = 0; q < kMaxSources; ++q) {
+							const int src = s_src[hb * kMaxSources + q];
+							if (src == INT32_MIN) break;
+							float v; int av;
+							if (src < 0) { v = segmax[-src - 1]; av = segarg[-src - 1]; }
+							else { v = D[(size_t)src * bs]; av = src; }
+							if (v > ubest) { ubest = v; uarg = av; }
+						}
+					}
 					float cm = -1.0f; int ca = hb;
 					for (int f1 = nh; f1 > 0; f1 -= CH) {
 						const int f0 = f1 > CH ? f1 - CH : 0;
@@ -761,14 +835,16 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 							const int f = f1 - 1 - k;
 							if (f >= f0) {
 								const int j = hb + f;
-								float best = -1.0f; int arg = -1;
-								for (int q = 0; q < kMaxSources; ++q) {
-									const int src = s_src[j * kMaxSources + q];
-									if (src == INT32_MIN) break;
-									float v; int av;
-									if (src < 0) { v = segmax[-src - 1]; av = segarg[-src - 1]; }
-									else { v = D[(size_t)src * bs]; av = src; }
-									if (v > best) { best = v; arg = av; }
+								float best = ubest; int arg = uarg;
+								if (!(flag & 2)) {
+									for (int q = 0; q < kMaxSources; ++q) {
+										const int src = s_src[j * kMaxSources + q];
+										if (src == INT32_MIN) break;
+										float v; int av;
+										if (src < 0) { v = segmax[-src - 1]; av = segarg[-src - 1]; }
+										else { v = D[(size_t)src * bs]; av = src; }
+										if (v > best) { best = v; arg = av; }
+									}
 								}
 								const float self = D[(size_t)j * bs];
 								float mx; int mv;
@@ -789,6 +865,14 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 			for (int j = 0; j < H; ++j) {
 				const float v = D[(size_t)j * bs];
 				if (v > mx) { mx = v; move = j; }
+			}
+			// traceback (:4503-4514); an HMM without predecessors keeps the path on itself
+			for (int i = 0; i <= rlen; ++i) labels[i] = 0;
+			if (move < 0) move = 0;
+			labels[len] = (uint8_t)move;
+			for (int i = len; i > 0; --i) {
+				if (s_src[move * kMaxSources] != INT32_MIN) move = path[((size_t)(i - 1) * H + move) * kBlock];
+				labels[i - 1] = (uint8_t)move;
 			}
 		} else {
 			// generic O(L*H^2) form, verbatim tie rules (:4453-4464)
@@ -814,13 +898,13 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 				const float v = (len >= 1) ? post[((size_t)(len - 1) * H + j) * kBlock] : 0.0f;
 				if (v > mx) { mx = v; move = j; }
 			}
-		}
-		for (int i = 0; i <= rlen; ++i) labels[i] = 0;
-		if (move < 0) move = 0;
-		labels[len] = (uint8_t)move;
-		for (int i = len; i > 0; --i) {
-			move = path[((size_t)(i - 1) * H + move) * kBlock];
-			labels[i - 1] = (uint8_t)move;
+			for (int i = 0; i <= rlen; ++i) labels[i] = 0;
+			if (move < 0) move = 0;
+			labels[len] = (uint8_t)move;
+			for (int i = len; i > 0; --i) {
+				move = path[((size_t)(i - 1) * H + move) * kBlock];
+				labels[i - 1] = (uint8_t)move;
+			}
 		}
 	}
 	if (!a.do_extract) return;
