@@ -1,0 +1,140 @@
+"""BASELINE.json configs 3, 4 and 5 at their real architecture shapes, through the C ABI:
+several waves of reads on the GPU, oracle parity on a sample spread over the waves, plus
+size-independent properties.  (Config 1 = tests/test_gold_dropin.py, config 2 = test_gpu_parity.py.)
+
+Reference limits honoured: config 3 uses 95 barcodes (1 + 2 + 96 + 1 = 100 HMMs,
+`float total_prob[100]`, barcode_hmm.c:4186); config 4 puts both index segments on read 1."""
+import numpy as np
+import pytest
+
+from cases import TAGS6_ED3, bits
+from refharness import background_logp
+from tagdust_b200 import synth
+from tagdust_b200.api import MODE_GET_LABEL, compile_architecture
+from test_gpu_parity import SCORE_KEYS, compare, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+BG = background_logp((2.5e6, 2.5e6, 2.5e6, 2.5e6, 1.0))
+WAVE = 148 * 512
+LINKER = "ACGTTGCAGTCA"
+
+
+def sample_parity(oracle, desc, codes, lens, gpu, n, step, **kw):
+    idx = np.concatenate([np.arange(0, n, step), np.arange(n - 24, n)])
+    ora = oracle.run(desc, MODE_GET_LABEL, codes[idx], lens[idx], threads=8, **kw)
+    sub = {k: v[idx] for k, v in gpu.items()}
+    rep = compare(sub, ora, lens[idx], MODE_GET_LABEL, "sample")
+    assert all(v == 0 for v in rep.values()), rep
+
+
+def test_cfg3_umi_linker_95_barcodes(gpu_ctx, oracle):
+    """-1 F:NNNNNNNN -2 S:<12 nt linker> -3 B:<95 barcodes> -4 R:N on 150 nt reads (H = 100, C = 8 + 24 + 576 + 1)."""
+    tags = TAGS6_ED3[:95]
+    segs = ["F:NNNNNNNN", "S:" + LINKER, "B:" + ",".join(tags), "R:N"]
+    desc = compile_architecture(segs, BG, 150.0, 150)
+    assert desc.total_hmms == 100
+    n = WAVE + 3001
+    codes, lens, truth = synth.make_reads(n, 150, [LINKER + t for t in tags], umi_len=8, error_rate=0.01, random_frac=0.05, seed=31)
+    kw = dict(threshold=1.5, minlen=16, dust=100)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, **kw)
+    ok = gpu["read_type"] == 0
+    model = truth >= 0
+    assert ok[model].mean() > 0.98
+    sel = ok & model
+    assert ((gpu["barcode"][sel] & 0xFFFF) == truth[sel]).mean() > 0.995
+    assert (gpu["barcode"][sel] >> 16 == 2).all()                       # segment index of the B segment
+    # UMI: 8 bases, 2 bits each, length byte 8 (extract_reads :3212-3215, :3262-3275)
+    fp = gpu["fingerprint"][sel]
+    assert ((fp & 0xFF) == 8).all()
+    umi = np.zeros(n, np.int64)
+    for k in range(8):
+        umi = (umi << 2) | (codes[:, k] & 3)
+    assert ((fp >> 8) == umi[sel]).mean() > 0.97                         # 1 % errors / indel-shifted labels allowed
+    assert np.all(np.abs(gpu["f_score"] - gpu["b_score"]) < 5e-2)
+    sample_parity(oracle, desc, codes, lens, gpu, n, 331, **kw)
+
+
+def test_cfg4_dual_index(gpu_ctx, oracle):
+    """-1 B:<24 I7 tags> -2 B:<16 I5 tags> -3 R:N on 150 nt reads (H = 43, C = 253); 384 combinations,
+    compared per segment through the labels (ri->barcode keeps only the last B segment, :3216-3225)."""
+    i7, i5 = TAGS6_ED3[:24], TAGS6_ED3[24:40]
+    segs = ["B:" + ",".join(i7), "B:" + ",".join(i5), "R:N"]
+    desc = compile_architecture(segs, BG, 150.0, 150)
+    assert desc.total_hmms == 43 and desc.total_columns == 253
+    n = WAVE + 2000
+    codes, lens, truth = synth.make_reads(n, 150, i7, second_barcodes=i5, error_rate=0.01, random_frac=0.05, seed=41)
+    kw = dict(threshold=1.5, minlen=16, dust=100)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, **kw)
+    ok = (gpu["read_type"] == 0) & (truth >= 0)
+    assert ok[truth >= 0].mean() > 0.98
+    lab = gpu["labels"][:, 1:151].astype(np.int32)
+    hmm_seg = np.asarray(desc.label) & 0xFFFF
+    hmm_idx = (np.asarray(desc.label) >> 16) & 0x7FFF
+    first = np.full(n, -1); second = np.full(n, -1)
+    for r in np.nonzero(ok)[0][:4000]:
+        s = hmm_seg[lab[r]]
+        a = lab[r][s == 0]; b = lab[r][s == 1]
+        if len(a): first[r] = hmm_idx[a[0]]
+        if len(b): second[r] = hmm_idx[b[0]]
+    chk = np.nonzero(ok)[0][:4000]
+    combo = first[chk] * 16 + second[chk]
+    assert (combo == truth[chk]).mean() > 0.99
+    assert ((gpu["barcode"][chk] & 0xFFFF) == second[chk]).all() and ((gpu["barcode"][chk] >> 16) == 1).all()
+    sample_parity(oracle, desc, codes, lens, gpu, n, 257, **kw)
+
+
+def candidate_architectures(n_arch):
+    """Distinct candidate architectures for library-prep detection (test_architectures.c): barcode sets of
+    different sizes, with/without UMI, linker, optional G, partial adapters.  Index 5 is the true one."""
+    out = []
+    sizes = [4, 8, 12, 16, 24, 32, 48, 64]
+    k = 0
+    while len(out) < n_arch:
+        nb = sizes[k % len(sizes)]
+        variant = (k // len(sizes)) % 8
+        tags = TAGS6_ED3[(k * 3) % 16:(k * 3) % 16 + nb]
+        b = "B:" + ",".join(tags)
+        segs = {
+            0: [b, "R:N"],
+            1: ["F:NNNN", b, "R:N"],
+            2: [b, "S:GGG", "R:N"],
+            3: ["O:N", b, "R:N"],
+            4: ["F:NNNNNNNN", "S:" + LINKER, b, "R:N"],
+            5: ["S:" + LINKER[:6], b, "R:N"],
+            6: [b, "R:N", "S:TTTTTT"],
+            7: ["G:G", b, "S:T", "R:N"],
+        }[variant]
+        out.append(segs)
+        k += 1
+    out[5] = ["B:" + ",".join(TAGS6_ED3[:48]), "R:N"]
+    assert len({tuple(s) for s in out}) == n_arch
+    return out
+
+
+def test_cfg5_architecture_detection(gpu_ctx, oracle):
+    """test_architectures: 64 candidate architectures scored by backward() over a read sample,
+    posteriors = per-thread float sums normalised with logsum (do_arch_comparison :2111-2148, merge :1994-2017)."""
+    archs = candidate_architectures(64)
+    descs = [compile_architecture(s, BG, 150.0, 150) for s in archs]
+    tags = TAGS6_ED3[:48]
+    n = 20000
+    codes, lens, _ = synth.make_reads_fast(n, 150, tags, error_rate=0.01, random_frac=0.05, seed=51)
+    models = [gpu_ctx.model(d, 150) for d in descs]
+    batch = gpu_ctx.batch(n, 150)
+    batch.append(codes, lens)
+    bs, post = gpu_ctx.arch_compare(models, batch, num_threads=8)
+    assert int(np.argmax(post)) == 5                                   # the generating architecture wins
+    assert np.isclose(np.exp(post.astype(np.float64)).sum(), 1.0, atol=1e-3)
+    # oracle parity on a prefix (b_score per (architecture, read) and the posteriors of that prefix)
+    m = 160
+    small = gpu_ctx.batch(m, 150)
+    small.append(codes[:m], lens[:m])
+    bs_s, post_s = gpu_ctx.arch_compare(models, small, num_threads=3)
+    want_bs, want_post = oracle.arch_compare(descs, codes[:m], lens[:m], threads=3)
+    assert np.array_equal(bits(bs_s), bits(want_bs))
+    assert np.array_equal(bits(post_s), bits(want_post))
+    assert np.array_equal(bits(bs[:, :m]), bits(want_bs))               # independent of the batch it was scored in
+    small.close(); batch.close()
+    for mo in models:
+        mo.close()
