@@ -25,6 +25,7 @@
 #include "barcode_hmm.h"
 
 #include "tagdust_b200.h"
+#include "shim.h"
 
 static tdg_context* g_ctx = NULL;
 static tdg_batch* g_batch = NULL;
@@ -60,9 +61,15 @@ static unsigned long long fnv(unsigned long long h, const void* p, size_t n)
 	return h;
 }
 
-/* struct model_bag -> tdg_model (flatten in segment -> hmm -> column order) */
-static tdg_model* get_model(struct model_bag* mb, struct parameters* param)
+tdg_context* tdg_shim_context(struct parameters* param)
 {
+	return ensure_ctx(param) == kslOK ? g_ctx : NULL;
+}
+
+/* struct model_bag -> tdg_model (flatten in segment -> hmm -> column order) */
+tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param)
+{
+	if (ensure_ctx(param) != kslOK) return NULL;
 	int S = mb->num_models, H = mb->total_hmm_num, C = 0, j, f, g, k, c = 0;
 	for (j = 0; j < S; j++) C += mb->model[j]->num_hmms * mb->model[j]->hmms[0]->num_columns;
 	char* seg_type = malloc(S + 1);
@@ -147,7 +154,7 @@ int run_pHMM(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, s
 		tdg_model** models = malloc(sizeof(tdg_model*) * ab->num_arch);
 		int max_len = 0;
 		for (i = 0; i < ab->num_arch; i++) {
-			models[i] = get_model(ab->archs[i], param);   /* NB: seg types come from param->read_structure; only
+			models[i] = tdg_shim_get_model(ab->archs[i], param);   /* NB: seg types come from param->read_structure; only
 			                                                 needed by extraction, not by backward() */
 			if (!models[i]) { free(models); return fail_msg(param, "tdg_model_create"); }
 			if (ab->archs[i]->current_dyn_length > max_len) max_len = ab->archs[i]->current_dyn_length;
@@ -164,7 +171,7 @@ int run_pHMM(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, s
 	}
 	if (mode != MODE_GET_LABEL && mode != MODE_GET_PROB) return kslFAIL; /* MODE_TRAIN: no live caller */
 
-	tdg_model* m = get_model(mb, param);
+	tdg_model* m = tdg_shim_get_model(mb, param);
 	if (!m) return fail_msg(param, "tdg_model_create");
 	if (load_batch(param, ri, numseq, 1) != kslOK) return kslFAIL;
 

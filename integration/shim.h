@@ -1,0 +1,11 @@
+/* shim.h -- pieces shared by the two reference-side bindings (run_phmm_gpu.c, controller_gpu.c). */
+#ifndef TDG_SHIM_H
+#define TDG_SHIM_H
+#include "tagdust_b200.h"
+struct parameters;
+struct model_bag;
+/* the process-wide GPU context (created on first use; NULL + param->errmsg on failure) */
+tdg_context* tdg_shim_context(struct parameters* param);
+/* struct model_bag -> tdg_model through a small content-keyed cache; seg types come from param->read_structure */
+tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param);
+#endif

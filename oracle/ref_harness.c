@@ -379,3 +379,49 @@ int refh_emit(struct model_bag* mb, int n_model, int n_random, int average_lengt
 }
 
 size_t refh_sizeof_read_info(void){ return sizeof(struct read_info); }
+
+/* ---------------- FASTQ reader (io_handler io.c:382 + read_fasta_fastq io.c:1684) ----------------
+ * Reads chunk number `chunk_index` (0-based) of `num_query` reads from `path` with the reference's own
+ * reader and flattens it: lens[n], codes/quals rows of `stride` bytes (quals all 0 when the reference
+ * left ri->qual NULL), names joined with '\n'.  Returns the number of reads in that chunk, -1 on error. */
+int refh_read_file_chunk(const char* path, int num_query, int chunk_index, int stride,
+                         int* lens, unsigned char* codes, unsigned char* quals, int* has_qual,
+                         char* names, size_t names_cap)
+{
+	struct parameters* param = calloc(1, sizeof(struct parameters));
+	struct read_info** ri = NULL;
+	FILE* file = NULL;
+	int numseq = 0, i, k;
+	size_t np = 0;
+	char* files[1];
+	refh_init();
+	files[0] = (char*)path;
+	param->infile = files;
+	param->infiles = 1;
+	param->num_query = num_query;
+	param->buffer = calloc(MSG_BUFFER_SIZE + 16, 1);
+	param->quiet_flag = 1;
+	ri = malloc_read_info(ri, num_query);
+	file = io_handler(file, 0, param);
+	for(k = 0; k <= chunk_index; k++){
+		if(read_fasta_fastq(ri, param, file, &numseq) != kslOK){ numseq = -1; break; }
+		if(!numseq) break;
+	}
+	*has_qual = 0;
+	for(i = 0; i < numseq; i++){
+		size_t nl = strlen(ri[i]->name);
+		lens[i] = ri[i]->len;
+		if(ri[i]->len + 1 > stride || np + nl + 1 > names_cap){ numseq = -1; break; }
+		memcpy(codes + (size_t)i * stride, ri[i]->seq, ri[i]->len + 1);
+		if(ri[i]->qual){ memcpy(quals + (size_t)i * stride, ri[i]->qual, ri[i]->len + 1); *has_qual = 1; }
+		memcpy(names + np, ri[i]->name, nl); np += nl;
+		names[np++] = '\n';
+	}
+	if(np < names_cap) names[np] = 0;
+	pclose(file);
+	free_read_info(ri, num_query);
+	free(param->buffer);
+	if(param->messages) free(param->messages);
+	free(param);
+	return numseq;
+}

@@ -1,16 +1,27 @@
-# usage: bash scripts/gpu_cli_e2e.sh <nreads>  -- CLI-level end to end: reference CLI + interposed run_pHMM on a simreads cfg2 file
+# usage: bash scripts/gpu_cli_e2e.sh <nreads> [ncmp]
+# CLI-level end to end on a simreads cfg2 file: FASTQ file -> drop-in binary (reference CLI + interposed
+# run_pHMM and hmm_controller_multiple) -> demultiplexed files; plus a byte comparison with the CPU reference
+# on a prefix of the file.
 set -x
 cd /root/repo
-N=${1:-2000000}
-W=/tmp/cli_e2e; mkdir -p $W gpurun_out
+N=${1:-4000000}
+NCMP=${2:-60000}
+W=/tmp/cli_e2e; rm -rf $W; mkdir -p $W gpurun_out
 REF=oracle/_ref
-( time $REF/simreads tests/golden/edittag_6nt_ed3.txt -seed 7 -sim_barnum 48 -sim_readlen 144 -sim_readlen_mod 0 -sim_numseq $N -sim_endloss 0 -sim_random_frac 0.05 -sim_error_rate 0.01 -o $W/syn48.fq ) 2>&1 | tail -4
-ls -la $W | head; nproc
-head -c 400 $W/syn48.fq_tagdust_arch.txt; echo
-( time integration/_build/tagdust_gpu -t $(nproc) -Q 1.5 -arch $W/syn48.fq_tagdust_arch.txt $W/syn48.fq -o $W/gpu_out ) > gpurun_out/cli_gpu.log 2>&1
-tail -5 gpurun_out/cli_gpu.log
-cat $W/gpu_out_logfile.txt | tail -30
-head -n 200000 $W/syn48.fq > $W/small.fq
-( time $REF/tagdust -t $(nproc) -Q 1.5 -arch $W/syn48.fq_tagdust_arch.txt $W/small.fq -o $W/cpu_out ) > gpurun_out/cli_cpu.log 2>&1
-tail -5 gpurun_out/cli_cpu.log
-cat $W/cpu_out_logfile.txt | tail -12
+$REF/simreads tests/golden/edittag_6nt_ed3.txt -seed 7 -sim_barnum 48 -sim_readlen 144 -sim_readlen_mod 0 -sim_numseq $N -sim_endloss 0 -sim_random_frac 0.05 -sim_error_rate 0.01 -o $W/syn48.fq > /dev/null 2>&1
+ls -la $W/syn48.fq; nproc
+ARCH=$W/syn48.fq_tagdust_arch.txt
+# (1) throughput of the whole tool, fixed threshold (no calibration phase) and with calibration
+for Q in "-Q 1.5" ""; do
+  /usr/bin/time -f "wall %e s  user %U  sys %S  maxrss %M KB" timeout 600 env TDG_VERBOSE=1 integration/_build/tagdust_gpu -t $(nproc) $Q -arch $ARCH $W/syn48.fq -o $W/gpu_full > $W/full.log 2>&1
+  echo "rc=$? Q='$Q'"; tail -4 $W/full.log; grep -E "total input|extracted|Threshold|threshold" $W/gpu_full_logfile.txt
+  rm -f $W/gpu_full*
+done
+# (2) byte comparison with the CPU reference on a prefix
+head -n $((NCMP*4)) $W/syn48.fq > $W/small.fq
+mkdir -p $W/cpu $W/gpu
+/usr/bin/time -f "cpu reference wall %e s" timeout 900 $REF/tagdust -t $(nproc) -Q 1.5 -arch $ARCH $W/small.fq -o $W/cpu/out > /dev/null 2>&1; echo rc=$?
+/usr/bin/time -f "gpu drop-in wall %e s" timeout 300 integration/_build/tagdust_gpu -t $(nproc) -Q 1.5 -arch $ARCH $W/small.fq -o $W/gpu/out > /dev/null 2>&1; echo rc=$?
+nd=0; for f in $W/cpu/*.fq; do cmp -s $f $W/gpu/$(basename $f) || { echo DIFF $(basename $f); nd=$((nd+1)); }; done
+echo "files compared: $(ls $W/cpu/*.fq | wc -l), differing: $nd"
+grep -E "total input|successfully" $W/cpu/out_logfile.txt $W/gpu/out_logfile.txt

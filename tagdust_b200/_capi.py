@@ -130,6 +130,71 @@ PROTOTYPES = {
     "tdg_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
+
+class FastqChunkC(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("max_len", C.c_int32),
+        ("len", c_int32_p),
+        ("seq_off", C.POINTER(C.c_uint64)),
+        ("codes", c_uint8_p),
+        ("qual", c_uint8_p),
+        ("name_off", C.POINTER(C.c_uint64)),
+        ("names", C.POINTER(C.c_char)),
+    ]
+
+
+class DemuxInputC(C.Structure):
+    _fields_ = [
+        ("path", C.c_char_p),
+        ("fasta", C.c_int32),
+        ("model", C.c_void_p),
+        ("num_read_segments", C.c_int32),
+        ("confidence_threshold", C.c_float),
+        ("max_seq_len", C.c_int32),
+    ]
+
+
+class DemuxJobC(C.Structure):
+    _fields_ = [
+        ("n_inputs", C.c_int32),
+        ("inputs", C.POINTER(DemuxInputC)),
+        ("barcode_input", C.c_int32),
+        ("num_alternatives", C.c_int32),
+        ("barcode_names", C.POINTER(C.c_char_p)),
+        ("outfile", C.c_char_p),
+        ("minlen", C.c_int32),
+        ("dust", C.c_int32),
+        ("matchstart", C.c_int32),
+        ("matchend", C.c_int32),
+        ("print_seq_finger", C.c_int32),
+        ("threads", C.c_int32),
+        ("chunk_reads", C.c_int32),
+    ]
+
+
+class DemuxStatsC(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "total_read", "num_EXTRACT_SUCCESS", "num_EXTRACT_FAIL_BAR_FINGER_NOT_FOUND", "num_EXTRACT_FAIL_READ_TOO_SHORT",
+        "num_EXTRACT_FAIL_AMBIGIOUS_BARCODE", "num_EXTRACT_FAIL_ARCHITECTURE_MISMATCH", "num_EXTRACT_FAIL_MATCHES_ARTIFACTS",
+        "num_EXTRACT_FAIL_LOW_COMPLEXITY", "long_sequence_events")] + [(k, C.c_double) for k in (
+            "seconds_parse", "seconds_gpu_wait", "seconds_write", "seconds_total")]
+
+
+#: every symbol include/tagdust_b200_stream.h declares
+STREAM_PROTOTYPES = {
+    "tdg_fastq_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "tdg_fastq_next": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(FastqChunkC)]),
+    "tdg_fastq_close": (None, [C.c_void_p]),
+    "tdg_batch_append_ragged": (C.c_int, [C.c_void_p, C.c_int, c_uint8_p, C.POINTER(C.c_uint64), c_int32_p, C.c_int]),
+    "tdg_format_rq": (C.c_int, [C.c_float, C.c_char_p]),
+    "tdg_demux_run": (C.c_int, [C.c_void_p, C.POINTER(DemuxJobC), C.POINTER(DemuxStatsC)]),
+    "tdg_model_max_len": (C.c_int, [C.c_void_p]),
+    "tdg_model_set_max_len": (C.c_int, [C.c_void_p, C.c_int]),
+    "tdg_model_num_hmms": (C.c_int, [C.c_void_p]),
+    "tdg_model_read_hmms": (C.c_int, [C.c_void_p, c_uint8_p]),
+}
+
 _lib = None
 
 
@@ -145,7 +210,7 @@ def load_library(path=None):
             f"{p} not found: build the CUDA library first "
             "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
     lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
-    for name, (res, args) in PROTOTYPES.items():
+    for name, (res, args) in list(PROTOTYPES.items()) + list(STREAM_PROTOTYPES.items()):
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args

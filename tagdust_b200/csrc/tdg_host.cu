@@ -16,7 +16,10 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
 #include "../../include/tagdust_b200.h"
+#include "../../include/tagdust_b200_stream.h"
 #include "tdg_device.h"
 
 using namespace tdg;
@@ -44,6 +47,11 @@ static int fail(int code, const char* fmt, ...)
 	} while (0)
 
 extern "C" const char* tdg_last_error(void) { return g_err.c_str(); }
+namespace tdg {
+int set_last_error(int code, const char* msg) { g_err = msg ? msg : ""; return code; }  // used by tdg_stream.cpp
+}
+// tdg_model_set_max_len() may run on another host thread than tdg_submit(): both take this lock
+static std::mutex g_model_mu;
 extern "C" const char* tdg_version(void) { return "tagdust_b200 0.1 (sm_100a; reference TagDust 2.33)"; }
 
 // ------------------------------------------------------------------------------------------
@@ -583,6 +591,52 @@ extern "C" int tdg_batch_append_records(tdg_batch* b, int n, const void* const* 
 	return TDG_OK;
 }
 
+// Ragged rows (one 0-terminated code string per read, as the FASTQ reader leaves them), packed on
+// `threads` host threads: reads are independent and a tile's 32 lanes are written by one thread.
+extern "C" int tdg_batch_append_ragged(tdg_batch* b, int n, const uint8_t* codes, const uint64_t* seq_off, const int32_t* len, int threads)
+{
+	if (!b || !codes || !seq_off || !len) return fail(TDG_EINVAL, "NULL argument");
+	if (n < 0 || b->n + n > b->max_reads) return fail(TDG_EINVAL, "batch overflow: %d + %d > %d", b->n, n, b->max_reads);
+	for (int i = 0; i < n; i++)
+		if (len[i] < 0 || len[i] > b->max_len) return fail(TDG_EINVAL, "read %d: length %d exceeds batch max_len %d", i, len[i], b->max_len);
+	const int first = b->n;
+	// every read owns its own 32-bit words of the tile layout, so any split is race-free
+	const int T = std::max(1, std::min(threads, n / 4096));
+	auto work = [&](int lo, int hi) { for (int i = lo; i < hi; i++) pack_read(b, first + i, codes + seq_off[i], len[i]); };
+	if (T <= 1) work(0, n);
+	else {
+		std::vector<std::thread> th;
+		const int per = (n + T - 1) / T;
+		for (int t = 1; t < T; t++) th.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+		work(0, std::min(n, per));
+		for (auto& x : th) x.join();
+	}
+	b->n += n;
+	return TDG_OK;
+}
+
+extern "C" int tdg_model_max_len(const tdg_model* m) { return m ? m->max_len : 0; }
+extern "C" int tdg_model_num_hmms(const tdg_model* m) { return m ? m->hm.H : 0; }
+extern "C" int tdg_model_set_max_len(tdg_model* m, int max_len)
+{
+	if (!m || max_len < 1) return fail(TDG_EINVAL, "bad argument");
+	std::lock_guard<std::mutex> model_lock(g_model_mu);
+	if (max_len <= m->max_len) return TDG_OK;
+	const HostModel& hm = m->hm;
+	const size_t W = (size_t)max_len + 2;
+	m->max_len = max_len;
+	m->slot_bytes_bwd = (size_t)hm.S * W * 4;
+	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
+	                     (size_t)max_len * hm.H;
+	return TDG_OK;
+}
+extern "C" int tdg_model_read_hmms(const tdg_model* m, uint8_t* is_read)
+{
+	if (!m || !is_read) return fail(TDG_EINVAL, "NULL argument");
+	for (int h = 0; h < m->hm.H; h++) is_read[h] = m->hm.seg_type[m->hm.label[h] & 0xFFFF] == 'R';
+	return TDG_OK;
+}
+
 extern "C" int tdg_plan_shards(int n_reads, int n_devices, int32_t* first, int32_t* count)
 {
 	if (n_reads < 0 || n_devices < 1 || !first || !count) return fail(TDG_EINVAL, "bad argument");
@@ -771,6 +825,7 @@ extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_ru
 	if (mode != TDG_MODE_GET_LABEL && mode != TDG_MODE_GET_PROB && mode != TDG_MODE_ARCH_COMP)
 		return fail(TDG_EINVAL, "unsupported mode %d (MODE_TRAIN has no live caller in the reference)", mode);
 	if (mode != TDG_MODE_ARCH_COMP && !p) return fail(TDG_EINVAL, "run params required");
+	std::lock_guard<std::mutex> model_lock(g_model_mu);
 	int rc = check_compat(m, b, p);
 	if (rc) return rc;
 	if (b->pending) return fail(TDG_EINVAL, "batch already submitted; call tdg_wait first");
@@ -867,6 +922,7 @@ extern "C" int tdg_decode_resident(tdg_context* ctx, tdg_model* m, int mode, con
                                    void* cuda_stream, int* n_launches)
 {
 	if (!ctx) return fail(TDG_EINVAL, "NULL context");
+	std::lock_guard<std::mutex> model_lock(g_model_mu);
 	int rc = check_compat(m, b, p);
 	if (rc) return rc;
 	int total = 0;

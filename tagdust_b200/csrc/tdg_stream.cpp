@@ -1,0 +1,739 @@
+// tdg_stream.cpp -- streaming FASTQ ingest + demultiplexed output around the GPU decode path
+// (include/tagdust_b200_stream.h).  Host-only C++; the GPU is reached through the public C ABI.
+//
+// Reference behaviour reproduced (files under the reference's src/):
+//   read_fasta_fastq()            io.c:1684-1815   line state machine, name/seq/qual up to the first
+//                                                  control character, nuc_code[] conversion
+//   io_handler()                  io.c:382-608     suffix rules, zcat/bzcat pipes
+//   hmm_controller_multiple()     barcode_hmm.c:243-384   per-chunk loop, cross-file merge, tallies
+//   run_rna_dust()/do_rna_dust()  barcode_hmm.c:2043, :2370   files whose architecture is a single R segment
+//   dust_sequences()              barcode_hmm.c:2407-2467
+//   make_extracted_read()         barcode_hmm.c:3325-3356
+//   print_all()                   io.c:757-1016    output naming, headers, spacer-split records
+//
+// Design: three stages on their own threads -- parse (block reads, one memchr pass to split
+// lines, then conversion/packing on a worker pool), GPU (tdg_submit of chunk k+1 is queued before
+// tdg_wait of chunk k), write (extraction rewrite + formatting on the pool into per-thread,
+// per-file buffers, flushed in thread order so every file keeps input order).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/tagdust_b200_stream.h"
+#include "tdg_device.h"
+
+namespace tdg {
+int set_last_error(int code, const char* msg);  // tdg_host.cu
+}
+
+namespace {
+
+constexpr int kMaxLine = 10000;  // tagdust2.h:96; fgets() hands out at most kMaxLine-1 characters per call
+
+double now_s()
+{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int failf(int code, const char* fmt, ...)
+{
+	char buf[768];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	return tdg::set_last_error(code, buf);
+}
+
+// fn(begin, end, thread_index) over [0, n) on up to `threads` threads (the caller is one of them)
+template <class F>
+void parallel_for(int threads, size_t n, size_t grain, F fn)
+{
+	int T = std::max(1, threads);
+	if (grain > 0) T = (int)std::min<size_t>(T, std::max<size_t>(1, n / grain));
+	if (T <= 1) { fn((size_t)0, n, 0); return; }
+	std::vector<std::thread> th;
+	const size_t per = (n + T - 1) / T;
+	for (int t = 1; t < T; t++) {
+		const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
+		th.emplace_back([=] { fn(b, e, t); });
+	}
+	fn((size_t)0, std::min(n, per), 0);
+	for (auto& x : th) x.join();
+}
+
+struct NucTable {
+	uint8_t code[256];
+	uint8_t ctl[256];
+	NucTable()
+	{
+		for (int i = 0; i < 256; i++) { code[i] = 4; ctl[i] = (i < 32 || i == 127) ? 1 : 0; }  // iscntrl() in the C locale
+		code[46] = 5;                                                                             // '.' (nuc_code.c:52)
+		code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['G'] = code['g'] = 2;
+		code['T'] = code['t'] = 3; code['U'] = code['u'] = 3;
+	}
+};
+const NucTable kNuc;
+
+bool has_suffix(const std::string& s, const char* suf)
+{
+	const size_t n = strlen(suf);
+	return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// parsed chunk storage
+// ------------------------------------------------------------------------------------------
+struct ParsedChunk {
+	int n = 0, max_len = 0;
+	bool fasta = false;
+	std::vector<int32_t> len;
+	std::vector<uint64_t> seq_off, name_off;
+	std::vector<uint8_t> codes, qual;
+	std::vector<char> names;
+	// line table of the sequential pass: offsets into the reader's text, piece lengths (without the newline)
+	struct Rec { uint64_t name, seq, qual; uint32_t name_n, seq_n, qual_n; uint8_t has_seq, has_qual; };
+	std::vector<Rec> recs;
+};
+
+struct tdg_fastq {
+	std::string path;
+	bool fasta = false;
+	// plain file: mmap; pipe: growing buffer
+	const char* map = nullptr; size_t map_len = 0; int fd = -1;
+	FILE* pipe = nullptr;
+	std::vector<char> buf;
+	size_t beg = 0, end = 0;   // unconsumed text [beg, end) of `text()`
+	bool eof = false;
+	int set = 0, seq_p = 0;    // read_fasta_fastq's flags; they persist across chunks like the FILE position does
+	ParsedChunk own;           // storage behind the public tdg_fastq_next
+	const char* text() const { return map ? map : buf.data(); }
+};
+
+static int reader_fill(tdg_fastq* f)
+{
+	// pipe only: append another block after `end`
+	const size_t block = (size_t)16 << 20;
+	if (f->buf.size() < f->end + block) f->buf.resize(std::max(f->buf.size() * 2, f->end + block));
+	const size_t got = fread(f->buf.data() + f->end, 1, block, f->pipe);
+	if (got == 0) {
+		if (ferror(f->pipe)) return failf(TDG_EIO, "read error on %s", f->path.c_str());
+		f->eof = true;
+	}
+	f->end += got;
+	return TDG_OK;
+}
+
+extern "C" int tdg_fastq_open(const char* path, int fasta, tdg_fastq** out)
+{
+	if (!path || !out) return failf(TDG_EINVAL, "tdg_fastq_open: NULL argument");
+	*out = nullptr;
+	const std::string p(path);
+	if (access(path, R_OK) != 0) return failf(TDG_EIO, "Error: Cannot find input file: %s", path);  // io.c:403
+	bool gz = false, bz = false, fa = false;
+	// suffix rules of io_handler (io.c:410-457)
+	if (has_suffix(p, ".gz")) gz = true;
+	if (has_suffix(p, ".bz2")) bz = true;
+	if (has_suffix(p, ".fa") || has_suffix(p, ".fasta") || has_suffix(p, ".fa.gz")) fa = true;
+	if (has_suffix(p, ".sam") || has_suffix(p, ".bam") || has_suffix(p, ".sam.gz") || has_suffix(p, ".bam.gz"))
+		return failf(TDG_EINVAL, "%s: SAM/BAM input is not handled by the streaming reader", path);
+	auto* f = new tdg_fastq();
+	f->path = p;
+	f->fasta = fasta < 0 ? fa : fasta != 0;
+	if (gz || bz) {
+		const char* tool = bz ? "bzcat" : "zcat";
+		if (gz && (access("/usr/bin/gzcat", X_OK) == 0 || access("/bin/gzcat", X_OK) == 0)) tool = "gzcat";
+		std::string cmd = std::string(tool) + " '" + p + "'";
+		f->pipe = popen(cmd.c_str(), "r");
+		if (!f->pipe) { delete f; return failf(TDG_EIO, "cannot run: %s", cmd.c_str()); }
+	} else {
+		f->fd = open(path, O_RDONLY);
+		if (f->fd < 0) { delete f; return failf(TDG_EIO, "cannot open %s", path); }
+		struct stat st;
+		if (fstat(f->fd, &st) != 0) { close(f->fd); delete f; return failf(TDG_EIO, "cannot stat %s", path); }
+		f->map_len = (size_t)st.st_size;
+		if (f->map_len > 0) {
+			void* m = mmap(nullptr, f->map_len, PROT_READ, MAP_PRIVATE, f->fd, 0);
+			if (m == MAP_FAILED) { close(f->fd); delete f; return failf(TDG_EIO, "cannot mmap %s", path); }
+			madvise(m, f->map_len, MADV_SEQUENTIAL);
+			f->map = (const char*)m;
+		} else {
+			f->map = "";
+		}
+		f->end = f->map_len;
+		f->eof = true;  // everything is addressable
+	}
+	*out = f;
+	return TDG_OK;
+}
+
+extern "C" void tdg_fastq_close(tdg_fastq* f)
+{
+	if (!f) return;
+	if (f->pipe) pclose(f->pipe);
+	if (f->map && f->map_len) munmap((void*)f->map, f->map_len);
+	if (f->fd >= 0) close(f->fd);
+	delete f;
+}
+
+// Sequential pass: split lines, run read_fasta_fastq's state machine, fill pc.recs.
+// Conversion pass: names, codes, qualities on the worker pool.
+static int parse_next(tdg_fastq* f, int max_reads, int threads, ParsedChunk& pc)
+{
+	pc.n = 0; pc.max_len = 0; pc.fasta = f->fasta;
+	pc.recs.clear();
+	if (max_reads < 1) return failf(TDG_EINVAL, "max_reads must be >= 1");
+	if (f->pipe && f->beg > 0) {  // compact the unconsumed tail to the front
+		memmove(f->buf.data(), f->buf.data() + f->beg, f->end - f->beg);
+		f->end -= f->beg; f->beg = 0;
+	}
+	size_t pos = f->beg;
+	bool done = false;
+	while (!done) {
+		const char* base = f->text();
+		const char* nl = (pos < f->end) ? (const char*)memchr(base + pos, '\n', std::min(f->end - pos, (size_t)kMaxLine - 1)) : nullptr;
+		size_t piece, next;
+		if (nl) { piece = (size_t)(nl - (base + pos)); next = pos + piece + 1; }
+		else if (f->end - pos >= (size_t)kMaxLine - 1) { piece = kMaxLine - 1; next = pos + piece; }  // fgets() splits long lines
+		else if (!f->eof) { int rc = reader_fill(f); if (rc) return rc; continue; }
+		else if (pos < f->end) { piece = f->end - pos; next = f->end; }  // last line without newline
+		else break;
+		const char c0 = piece ? base[pos] : '\n';
+		if ((c0 == '@' || c0 == '>') && !f->set) {
+			ParsedChunk::Rec r;
+			memset(&r, 0, sizeof r);
+			r.name = pos; r.name_n = (uint32_t)piece;
+			pc.recs.push_back(r);
+			f->seq_p = 1; f->set = 1;
+		} else if (c0 == '+' && !f->set) {
+			f->seq_p = 0; f->set = 1;
+		} else {
+			if (f->set && !pc.recs.empty()) {
+				ParsedChunk::Rec& r = pc.recs.back();
+				if (f->seq_p) { r.seq = pos; r.seq_n = (uint32_t)piece; r.has_seq = 1; }
+				else { r.qual = pos; r.qual_n = (uint32_t)piece; r.has_qual = 1; }
+			}
+			f->set = 0;
+		}
+		pos = next;
+		if ((int)pc.recs.size() == max_reads) {  // io.c:1797-1808: the chunk ends once its last entry is complete
+			const ParsedChunk::Rec& r = pc.recs.back();
+			if ((!f->fasta && r.has_qual) || (f->fasta && r.has_seq)) done = true;
+		}
+	}
+	f->beg = pos;
+	const int n = (int)pc.recs.size();
+	pc.n = n;
+	if (n == 0) return TDG_OK;
+	// offsets (upper bounds: the piece lengths; the real lengths stop at the first control character)
+	pc.len.resize(n); pc.seq_off.resize(n); pc.name_off.resize((size_t)n + 1);
+	uint64_t so = 0, no = 0;
+	for (int r = 0; r < n; r++) {
+		const ParsedChunk::Rec& R = pc.recs[r];
+		if (!R.has_seq) return failf(TDG_EFORMAT, "%s: entry %d has no sequence line", f->path.c_str(), r);
+		if (!f->fasta && !R.has_qual) return failf(TDG_EFORMAT, "%s: entry %d has no quality line", f->path.c_str(), r);
+		pc.seq_off[r] = so; so += (uint64_t)R.seq_n + 1;
+		pc.name_off[r] = no; no += (uint64_t)R.name_n;  // '@' dropped, NUL added
+	}
+	pc.name_off[n] = no;
+	pc.codes.resize(so);
+	if (!f->fasta) pc.qual.resize(so); else pc.qual.clear();
+	pc.names.resize(no);
+	const char* base = f->text();
+	std::atomic<int> bad{-1};
+	std::vector<int> tmax((size_t)std::max(1, threads), 0);
+	const bool fasta = f->fasta;
+	parallel_for(threads, (size_t)n, 2048, [&](size_t b, size_t e, int t) {
+		int mx = 0;
+		for (size_t r = b; r < e; r++) {
+			const ParsedChunk::Rec& R = pc.recs[r];
+			// name: line[1..] up to the first control character (io.c:1723-1735)
+			{
+				const uint8_t* s = (const uint8_t*)base + R.name + 1;
+				char* d = pc.names.data() + pc.name_off[r];
+				uint32_t i = 0;
+				const uint32_t lim = R.name_n ? R.name_n - 1 : 0;
+				while (i < lim && !kNuc.ctl[s[i]]) { d[i] = (char)s[i]; i++; }
+				d[i] = 0;
+			}
+			uint8_t* c = pc.codes.data() + pc.seq_off[r];
+			const uint8_t* s = (const uint8_t*)base + R.seq;
+			uint32_t i = 0;
+			while (i < R.seq_n && !kNuc.ctl[s[i]]) { c[i] = kNuc.code[s[i]]; i++; }
+			c[i] = 0;
+			pc.len[r] = (int32_t)i;
+			if ((int)i > mx) mx = (int)i;
+			if (!fasta) {
+				uint8_t* q = pc.qual.data() + pc.seq_off[r];
+				const uint8_t* s2 = (const uint8_t*)base + R.qual;
+				uint32_t k = 0;
+				while (k < R.qual_n && !kNuc.ctl[s2[k]]) { if (k <= i) q[k] = s2[k]; k++; }
+				if (k != i) { int exp = -1; bad.compare_exchange_strong(exp, (int)r); }
+				q[i] = 0;
+			}
+		}
+		tmax[t] = std::max(tmax[t], mx);
+	});
+	if (bad.load() >= 0) return failf(TDG_EFORMAT, "ERROR: Length of sequence and base qualities differ!.");  // io.c:1770
+	for (int v : tmax) pc.max_len = std::max(pc.max_len, v);
+	return TDG_OK;
+}
+
+extern "C" int tdg_fastq_next(tdg_fastq* f, int max_reads, int threads, tdg_fastq_chunk* chunk)
+{
+	if (!f || !chunk) return failf(TDG_EINVAL, "tdg_fastq_next: NULL argument");
+	int rc = parse_next(f, max_reads, threads, f->own);
+	memset(chunk, 0, sizeof *chunk);
+	if (rc) return rc;
+	const ParsedChunk& pc = f->own;
+	chunk->n = pc.n; chunk->max_len = pc.max_len;
+	if (pc.n) {
+		chunk->len = pc.len.data(); chunk->seq_off = pc.seq_off.data(); chunk->codes = pc.codes.data();
+		chunk->qual = pc.fasta ? nullptr : pc.qual.data();
+		chunk->name_off = pc.name_off.data(); chunk->names = pc.names.data();
+	}
+	return TDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// formatting
+// ------------------------------------------------------------------------------------------
+// `%0.2f` of (double)mapq.  A float times 100 is exact in double (24 + 7 significant bits), so
+// rint() under the default round-to-nearest-even mode gives the digits glibc prints.
+extern "C" int tdg_format_rq(float mapq, char* out)
+{
+	const double v = (double)mapq;
+	if (!std::isfinite(v) || std::fabs(v) >= 1e15) return sprintf(out, "%0.2f", v);
+	char* p = out;
+	if (std::signbit(v)) *p++ = '-';
+	uint64_t n = (uint64_t)std::rint(std::fabs(v) * 100.0);
+	const uint64_t ip = n / 100;
+	const unsigned fr = (unsigned)(n % 100);
+	char tmp[24];
+	int k = 0;
+	uint64_t x = ip;
+	do { tmp[k++] = (char)('0' + x % 10); x /= 10; } while (x);
+	while (k) *p++ = tmp[--k];
+	*p++ = '.';
+	*p++ = (char)('0' + fr / 10);
+	*p++ = (char)('0' + fr % 10);
+	*p = 0;
+	return (int)(p - out);
+}
+
+namespace {
+
+inline char* put_int(char* p, int v)
+{
+	unsigned u = (unsigned)v;
+	if (v < 0) { *p++ = '-'; u = 0u - u; }
+	char tmp[12];
+	int k = 0;
+	do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+	while (k) *p++ = tmp[--k];
+	return p;
+}
+
+// dust_sequences (barcode_hmm.c:2407-2467) on one read; `seq` is 0-terminated like ri->seq
+bool dust_low_complexity(const uint8_t* seq, int rlen, int dust_cut)
+{
+	double triplet[64];
+	for (int j = 0; j < 64; j++) triplet[j] = 0.0;
+	int c = 0;
+	while (seq[c] == 65) c++;
+	int key = ((seq[c] & 0x3) << 2) | (seq[c + 1] & 0x3);
+	int len = rlen;
+	if (len > 64) len = 64;
+	c += 2;
+	for (int j = c; j < len; j++) {
+		if (seq[j] == 65) break;
+		key = key << 2 | (seq[j] & 0x3);
+		triplet[key & 0x3F]++;
+		c++;
+	}
+	double s = 0.0;
+	for (int j = 0; j < 64; j++) s += triplet[j] * (triplet[j] - 1.0) / 2.0;
+	s = s / (double)(c - 3) * 10.0;
+	return s > dust_cut;
+}
+
+struct OutBuf {
+	std::vector<char> d;
+	size_t n = 0;
+	char* grow(size_t need)
+	{
+		if (n + need > d.size()) d.resize(std::max(d.size() * 2, n + need + (1u << 16)));
+		return d.data() + n;
+	}
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// the pipeline
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Slot {
+	std::vector<ParsedChunk> pc;          // per input
+	std::vector<tdg_batch*> batch;        // per input (nullptr without model)
+	std::vector<int> batch_reads, batch_len;
+	std::vector<tdg_result> res;          // per input, valid after the GPU stage
+	int n = 0;
+	bool last = false;
+};
+
+template <class T>
+struct Queue {
+	std::mutex m; std::condition_variable cv; std::deque<T> q; bool closed = false;
+	void push(T v) { { std::lock_guard<std::mutex> l(m); q.push_back(v); } cv.notify_all(); }
+	void close() { { std::lock_guard<std::mutex> l(m); closed = true; } cv.notify_all(); }
+	bool pop(T& v)
+	{
+		std::unique_lock<std::mutex> l(m);
+		cv.wait(l, [&] { return !q.empty() || closed; });
+		if (q.empty()) return false;
+		v = q.front(); q.pop_front();
+		return true;
+	}
+};
+
+struct Shared {
+	std::mutex m;
+	int code = TDG_OK;
+	std::string msg;
+	std::atomic<bool> failed{false};
+	void fail(int c, const char* s)
+	{
+		std::lock_guard<std::mutex> l(m);
+		if (code == TDG_OK) { code = c; msg = s ? s : ""; }
+		failed = true;
+	}
+};
+
+}  // namespace
+
+extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_demux_stats* stats)
+{
+	if (!job || !stats) return failf(TDG_EINVAL, "tdg_demux_run: NULL argument");
+	memset(stats, 0, sizeof *stats);
+	const int NI = job->n_inputs;
+	if (NI < 1 || !job->inputs || !job->outfile) return failf(TDG_EINVAL, "tdg_demux_run: no inputs / no output prefix");
+	bool any_model = false;
+	for (int i = 0; i < NI; i++) any_model |= job->inputs[i].model != nullptr;
+	if (any_model && !ctx) return failf(TDG_EINVAL, "tdg_demux_run: a GPU context is required");
+	const int threads = std::max(1, job->threads);
+	const int chunk_reads = job->chunk_reads > 0 ? job->chunk_reads : 4 * 148 * 512;
+	const int nalt = job->num_alternatives;
+	if (nalt < 2) return failf(TDG_EINVAL, "num_alternatives must be >= 2");
+	const double t_start = now_s();
+
+	// ---- output files (print_all, io.c:822-915): all of them exist afterwards, even when empty
+	int num_out_reads = 0;
+	std::vector<int> base_file(NI, 0);
+	for (int i = 0; i < NI; i++) { base_file[i] = nalt * num_out_reads; num_out_reads += job->inputs[i].num_read_segments; }
+	const int num_outfiles = nalt * num_out_reads;
+	if (num_outfiles == 0)
+		return failf(TDG_EINVAL, "ERROR: No output files to create. Input sequences may not contain extractable reads or may not match the expected architecture.");
+	std::vector<FILE*> files((size_t)num_outfiles, nullptr);
+	auto close_files = [&] { for (FILE* f : files) if (f) fclose(f); };
+	{
+		const bool bc = job->barcode_names != nullptr && job->barcode_input >= 0;
+		char name[4096];
+		int c = 0;
+		for (int i = 0; i < num_out_reads; i++) {
+			for (int j = 0; j < nalt; j++) {
+				const bool un = (j == nalt - 1);
+				if (bc) {
+					if (un) { if (num_out_reads > 1) snprintf(name, sizeof name, "%s_un_READ%d.fq", job->outfile, i + 1); else snprintf(name, sizeof name, "%s_un.fq", job->outfile); }
+					else if (num_out_reads > 1) snprintf(name, sizeof name, "%s_BC_%s_READ%d.fq", job->outfile, job->barcode_names[j], i + 1);
+					else snprintf(name, sizeof name, "%s_BC_%s.fq", job->outfile, job->barcode_names[j]);
+				} else {
+					// two alternatives: the extracted file and the `un` file (io.c:889-914)
+					if (un) { if (num_out_reads > 1) snprintf(name, sizeof name, "%s_un_READ%d.fq", job->outfile, i + 1); else snprintf(name, sizeof name, "%s_un.fq", job->outfile); }
+					else if (j == 0) { if (num_out_reads > 1) snprintf(name, sizeof name, "%s_READ%d.fq", job->outfile, i + 1); else snprintf(name, sizeof name, "%s.fq", job->outfile); }
+					else { c++; continue; }
+				}
+				files[c] = fopen(name, "w");
+				if (!files[c]) { close_files(); return failf(TDG_EIO, "Failed to open file:%s", name); }
+				c++;
+			}
+		}
+	}
+
+	// ---- readers
+	std::vector<tdg_fastq*> rd((size_t)NI, nullptr);
+	auto close_readers = [&] { for (auto* r : rd) tdg_fastq_close(r); };
+	for (int i = 0; i < NI; i++) {
+		int rc = tdg_fastq_open(job->inputs[i].path, job->inputs[i].fasta, &rd[i]);
+		if (rc) { close_readers(); close_files(); return rc; }
+	}
+	// per-model "is this HMM in an R segment" tables
+	std::vector<std::vector<uint8_t>> is_read((size_t)NI);
+	for (int i = 0; i < NI; i++)
+		if (job->inputs[i].model) {
+			is_read[i].resize((size_t)tdg_model_num_hmms(job->inputs[i].model));
+			tdg_model_read_hmms(job->inputs[i].model, is_read[i].data());
+		}
+
+	constexpr int NSLOT = 4;
+	std::vector<Slot> slots(NSLOT);
+	for (auto& s : slots) { s.pc.resize(NI); s.batch.assign(NI, nullptr); s.batch_reads.assign(NI, 0); s.batch_len.assign(NI, 0); s.res.resize(NI); }
+	Queue<int> q_free, q_gpu, q_write;
+	for (int k = 0; k < NSLOT; k++) q_free.push(k);
+	Shared sh;
+	std::atomic<int64_t> long_events{0};
+	double sec_parse = 0, sec_gpu = 0, sec_write = 0;
+
+	// ---- stage 1: parse + pack
+	std::thread t_parse([&] {
+		std::vector<int> run_max(NI);
+		for (int i = 0; i < NI; i++) run_max[i] = job->inputs[i].max_seq_len;
+		for (;;) {
+			int k;
+			if (!q_free.pop(k) || sh.failed) break;
+			Slot& s = slots[k];
+			const double t0 = now_s();
+			bool ok = true;
+			for (int i = 0; i < NI && ok; i++) {
+				if (parse_next(rd[i], chunk_reads, threads, s.pc[i]) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
+			}
+			if (!ok) break;
+			for (int i = 0; i + 1 < NI && ok; i++)
+				for (int j = i + 1; j < NI && ok; j++)
+					if (s.pc[i].n != s.pc[j].n) {  // barcode_hmm.c:258-268
+						char b[1024];
+						snprintf(b, sizeof b, "Input File:%s and %s differ in number of entries.", job->inputs[i].path, job->inputs[j].path);
+						sh.fail(TDG_EFORMAT, b); ok = false;
+					}
+			if (!ok) break;
+			s.n = s.pc[0].n;
+			s.last = (s.n == 0);
+			if (!s.last) {
+				for (int i = 0; i < NI && ok; i++) {
+					ParsedChunk& pc = s.pc[i];
+					// barcode_hmm.c:293-309: every read at least as long as the running maximum rebuilds the model
+					int64_t ev = 0;
+					int mx = run_max[i];
+					for (int r = 0; r < pc.n; r++) if (pc.len[r] >= mx) { mx = pc.len[r]; ev++; }
+					run_max[i] = mx;
+					long_events += ev;
+					tdg_model* m = job->inputs[i].model;
+					if (!m) continue;
+					int need = pc.max_len;
+					if (job->matchstart != -1 || job->matchend != -1) need = std::max(need, job->matchend);
+					if (need > tdg_model_max_len(m)) tdg_model_set_max_len(m, need + 10);
+					if (!s.batch[i] || s.batch_reads[i] < pc.n || s.batch_len[i] < pc.max_len) {
+						if (s.batch[i]) tdg_batch_destroy(s.batch[i]);
+						s.batch[i] = nullptr;
+						s.batch_reads[i] = std::max(s.batch_reads[i], std::max(pc.n, std::min(chunk_reads, 1 << 24)));
+						s.batch_len[i] = std::max(s.batch_len[i], pc.max_len);
+						if (tdg_batch_create(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; break; }
+					}
+					tdg_batch_clear(s.batch[i]);
+					if (tdg_batch_append_ragged(s.batch[i], pc.n, pc.codes.data(), pc.seq_off.data(), pc.len.data(), threads) != TDG_OK) {
+						sh.fail(TDG_EINVAL, tdg_last_error()); ok = false;
+					}
+				}
+			}
+			sec_parse += now_s() - t0;
+			if (!ok) break;
+			q_gpu.push(k);
+			if (s.last) break;
+		}
+		q_gpu.close();
+	});
+
+	// ---- stage 2: GPU (submit of chunk k+1 is queued before the wait on chunk k)
+	std::thread t_gpu([&] {
+		int prev = -1;
+		auto finish = [&](int k) -> bool {
+			Slot& s = slots[k];
+			const double t0 = now_s();
+			for (int i = 0; i < NI; i++)
+				if (job->inputs[i].model && !s.last)
+					if (tdg_wait(s.batch[i], &s.res[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); return false; }
+			sec_gpu += now_s() - t0;
+			q_write.push(k);
+			return true;
+		};
+		for (;;) {
+			int k;
+			if (!q_gpu.pop(k)) break;
+			if (sh.failed) break;
+			Slot& s = slots[k];
+			bool ok = true;
+			if (!s.last)
+				for (int i = 0; i < NI && ok; i++) {
+					tdg_model* m = job->inputs[i].model;
+					if (!m) continue;
+					tdg_run_params rp;
+					rp.confidence_threshold = job->inputs[i].confidence_threshold;
+					rp.minlen = job->minlen; rp.matchstart = job->matchstart; rp.matchend = job->matchend;
+					rp.dust = job->dust; rp.want_labels = 1;
+					if (tdg_submit(ctx, m, TDG_MODE_GET_LABEL, &rp, s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; }
+				}
+			if (!ok) break;
+			if (prev >= 0 && !finish(prev)) { prev = -1; break; }
+			prev = k;
+		}
+		if (prev >= 0 && !sh.failed) finish(prev);
+		q_write.close();
+	});
+
+	// ---- stage 3: post-process + write
+	std::thread t_write([&] {
+		std::vector<std::vector<OutBuf>> ob((size_t)threads, std::vector<OutBuf>((size_t)num_outfiles));
+		std::vector<std::vector<int64_t>> tally((size_t)threads, std::vector<int64_t>(8, 0));
+		for (;;) {
+			int k;
+			if (!q_write.pop(k)) break;
+			Slot& s = slots[k];
+			if (s.last || sh.failed) { q_free.push(k); if (s.last) break; continue; }
+			const double t0 = now_s();
+			const int n = s.n;
+			for (auto& v : ob) for (auto& b : v) b.n = 0;
+			parallel_for(threads, (size_t)n, 1024, [&](size_t b, size_t e, int t) {
+				static const char alphabet[] = "ACGTNN";
+				std::vector<OutBuf>& out = ob[t];
+				std::vector<int64_t>& tl = tally[t];
+				std::vector<int32_t> rt((size_t)NI), fpv((size_t)NI);
+				std::vector<float> mq((size_t)NI);
+				char fseq[260];
+				for (size_t r = b; r < e; r++) {
+					// per file: read_type / barcode / fingerprint / mapq and the in-place extraction rewrite
+					int merged = -100000, barcode = -1;
+					for (int i = 0; i < NI; i++) {
+						ParsedChunk& pc = s.pc[i];
+						uint8_t* seq = pc.codes.data() + pc.seq_off[r];
+						uint8_t* ql = pc.fasta ? nullptr : pc.qual.data() + pc.seq_off[r];
+						const int len = pc.len[r];
+						if (job->inputs[i].model) {
+							const tdg_result& R = s.res[i];
+							rt[i] = R.read_type[r]; fpv[i] = R.fingerprint[r]; mq[i] = R.mapq[r];
+							if (i == job->barcode_input) barcode = R.barcode[r];
+							if (R.extracted[r]) {  // make_extracted_read: everything outside R segments becomes the spacer 65
+								const uint8_t* lab = R.labels + (size_t)r * R.label_stride;
+								const uint8_t* isr = is_read[i].data();
+								for (int j = 0; j < len; j++)
+									if (!isr[lab[j + 1]]) { seq[j] = 65; if (ql) ql[j] = 65; }
+							}
+						} else {
+							rt[i] = TDG_EXTRACT_SUCCESS; fpv[i] = -1; mq[i] = -1.0f;  // do_rna_dust + clear_read_info (io.c:2063-2093)
+							if (job->dust && dust_low_complexity(seq, len, job->dust)) rt[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
+						}
+						merged = std::max(merged, rt[i]);
+					}
+					switch (merged) {  // barcode_hmm.c:358-382
+						case TDG_EXTRACT_SUCCESS: tl[0]++; break;
+						case TDG_EXTRACT_FAIL_BAR_FINGER_NOT_FOUND: tl[1]++; break;
+						case TDG_EXTRACT_FAIL_READ_TOO_SHORT: tl[2]++; break;
+						case TDG_EXTRACT_FAIL_ARCHITECTURE_MISMATCH: tl[4]++; break;
+						case TDG_EXTRACT_FAIL_MATCHES_ARTIFACTS: tl[5]++; tl[6]++; break;  // falls through in the reference
+						case TDG_EXTRACT_FAIL_LOW_COMPLEXITY: tl[6]++; break;
+						default: tl[5]++; break;
+					}
+					const int sel = (merged == TDG_EXTRACT_SUCCESS) ? (barcode != -1 ? (barcode & 0xFF) : 0) : nalt - 1;
+					for (int i = 0; i < NI; i++) {
+						if (!job->inputs[i].num_read_segments) continue;
+						const ParsedChunk& pc = s.pc[i];
+						const uint8_t* seq = pc.codes.data() + pc.seq_off[r];
+						const uint8_t* ql = pc.fasta ? nullptr : pc.qual.data() + pc.seq_off[r];
+						const int len = pc.len[r];
+						const char* name = pc.names.data() + pc.name_off[r];
+						const size_t name_len = strlen(name);
+						int f = base_file[i] + sel;
+						int g = 0;
+						while (g < len) {
+							while (g < len && seq[g] >= 5) g++;
+							int h = g;
+							while (h < len && seq[h] < 5) h++;
+							if (h == g) break;
+							const bool more = h < len;  // a spacer follows: the next run goes to the next READ file
+							if (f >= 0 && f < num_outfiles && files[f]) {
+								const int run = h - g;
+								char* p = out[f].grow(name_len + 2 * (size_t)run + 320);
+								char* p0 = p;
+								*p++ = '@';
+								memcpy(p, name, name_len); p += name_len;
+								if (fpv[i] != -1) {
+									memcpy(p, ";FP:", 4); p += 4;
+									if (job->print_seq_finger) {  // get_finger_seq, io.c:1018-1029
+										int key = fpv[i];
+										const int fl = key & 0xFF;
+										key >>= 8;
+										for (int q = 0; q < fl; q++) { fseq[fl - q - 1] = "ACGTN"[key & 0x3]; key >>= 2; }
+										memcpy(p, fseq, (size_t)fl); p += fl;
+									} else p = put_int(p, fpv[i]);
+								}
+								memcpy(p, ";RQ:", 4); p += 4;
+								p += tdg_format_rq(mq[i], p);
+								*p++ = '\n';
+								for (int q = g; q < h; q++) *p++ = alphabet[seq[q]];
+								*p++ = '\n'; *p++ = '+'; *p++ = '\n';
+								if (ql) { memcpy(p, ql + g, (size_t)run); p += run; }
+								else { memset(p, '.', (size_t)run); p += run; }
+								*p++ = '\n';
+								out[f].n += (size_t)(p - p0);
+							}
+							if (more) f += nalt;
+							g = h;
+						}
+					}
+				}
+			});
+			for (int f = 0; f < num_outfiles; f++) {
+				if (!files[f]) continue;
+				for (int t = 0; t < threads; t++) {
+					OutBuf& b = ob[t][f];
+					if (b.n && fwrite(b.d.data(), 1, b.n, files[f]) != b.n) { sh.fail(TDG_EIO, "write error on an output file"); break; }
+				}
+			}
+			stats->total_read += n;
+			sec_write += now_s() - t0;
+			q_free.push(k);
+		}
+		for (auto& tl : tally) {
+			stats->num_EXTRACT_SUCCESS += tl[0];
+			stats->num_EXTRACT_FAIL_BAR_FINGER_NOT_FOUND += tl[1];
+			stats->num_EXTRACT_FAIL_READ_TOO_SHORT += tl[2];
+			stats->num_EXTRACT_FAIL_ARCHITECTURE_MISMATCH += tl[4];
+			stats->num_EXTRACT_FAIL_MATCHES_ARTIFACTS += tl[5];
+			stats->num_EXTRACT_FAIL_LOW_COMPLEXITY += tl[6];
+		}
+		q_free.close();
+	});
+
+	t_parse.join();
+	if (sh.failed) { q_gpu.close(); q_free.close(); }
+	t_gpu.join();
+	if (sh.failed) { q_write.close(); q_free.close(); }
+	t_write.join();
+	for (auto& s : slots) for (auto* b : s.batch) if (b) tdg_batch_destroy(b);
+	close_readers();
+	close_files();
+	stats->long_sequence_events = long_events.load();
+	stats->seconds_parse = sec_parse; stats->seconds_gpu_wait = sec_gpu; stats->seconds_write = sec_write;
+	stats->seconds_total = now_s() - t_start;
+	if (sh.failed) return tdg::set_last_error(sh.code, sh.msg.c_str());
+	return TDG_OK;
+}

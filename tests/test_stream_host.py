@@ -1,0 +1,211 @@
+"""CPU tests of the streaming layer (include/tagdust_b200_stream.h): the FASTQ/FASTA reader against
+the reference's own io_handler + read_fasta_fastq (through oracle/_ref), the %0.2f formatter
+against printf, and the host-only path of the demultiplexer (architectures that are a single R
+segment never reach the GPU: run_rna_dust, barcode_hmm.c:312-318) against the reference CLI."""
+import ctypes as C
+import filecmp
+import glob
+import gzip
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from refharness import REF_SO, have_ref
+from tagdust_b200 import _capi
+from tagdust_b200.api import TagdustError
+from tagdust_b200.stream import FastqReader, demux_run, format_rq
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def test_stream_header_symbols_exported():
+    lib = _capi.load_library()
+    hdr = open(os.path.join(ROOT, "include", "tagdust_b200_stream.h")).read()
+    declared = set(re.findall(r"\b(tdg_[a-z0-9_]+)\s*\(", hdr))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/tagdust_b200_stream.h but not exported"
+    assert declared == set(_capi.STREAM_PROTOTYPES), declared ^ set(_capi.STREAM_PROTOTYPES)
+
+
+def test_format_rq_matches_printf():
+    rng = np.random.default_rng(3)
+    vals = list(rng.uniform(0, 40, 20000).astype(np.float32)) + list(rng.uniform(-2, 2, 2000).astype(np.float32))
+    # exact ties of the third decimal, signed zeros, large and tiny values, the reference's constants
+    vals += [np.float32(x) for x in (0.125, 0.375, 0.625, 0.875, 2.5, 1.005, 39.995, 40.0, 0.0, -0.0, -1.0, -0.001, 0.005,
+                                     0.015, 0.025, 1e-9, 123456.789, 9999999.0, 3.0386538505554199, 1.7987838983535767)]
+    for k in range(0, 4000):
+        vals.append(np.float32(k / 8.0 + 0.125))
+    for v in vals:
+        assert format_rq(float(v)) == "%0.2f" % float(v), float(v)
+
+
+def write_fastq(path, recs, crlf=False, trailing_newline=True):
+    eol = "\r\n" if crlf else "\n"
+    txt = eol.join(f"@{n}{eol}{s}{eol}+{eol}{q}" for n, s, q in recs)
+    if trailing_newline:
+        txt += eol
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "wt", newline="") as fh:
+        fh.write(txt)
+
+
+def random_records(rng, n, lo=1, hi=200, exotic=False):
+    alpha = "ACGTN" + ("acgtnRYK.U" if exotic else "")
+    recs = []
+    for k in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        seq = "".join(rng.choice(list(alpha), size=L))
+        qual = "".join(chr(int(c)) for c in rng.integers(33, 75, size=L))
+        if exotic and k % 7 == 0:
+            qual = "@" + qual[1:]          # quality lines may start with '@' or '+'
+        if exotic and k % 11 == 0:
+            qual = "+" + qual[1:]
+        name = f"read{k}:{rng.integers(1, 9)}:{rng.integers(1000, 9999)} 1:N:0:{k % 5}" if k % 3 else f"r{k};x=1\tafter_tab"
+        recs.append((name, seq, qual))
+    return recs
+
+
+class RefReader:
+    def __init__(self):
+        self.L = C.CDLL(REF_SO)
+        self.L.refh_read_file_chunk.restype = C.c_int
+
+    def chunk(self, path, num_query, index, stride=400):
+        lens = np.zeros(num_query, np.int32)
+        codes = np.zeros((num_query, stride), np.uint8)
+        quals = np.zeros((num_query, stride), np.uint8)
+        hq = C.c_int(0)
+        names = C.create_string_buffer(num_query * 200 + 16)
+        n = self.L.refh_read_file_chunk(str(path).encode(), num_query, index, stride, lens.ctypes.data_as(C.c_void_p),
+                                        codes.ctypes.data_as(C.c_void_p), quals.ctypes.data_as(C.c_void_p), C.byref(hq),
+                                        names, C.c_size_t(len(names)))
+        assert n >= 0
+        nm = names.value.split(b"\n")[:n]
+        return n, lens[:n], codes[:n], quals[:n], bool(hq.value), nm
+
+
+def assert_chunk_equal(mine, ref):
+    n, lens, codes, quals, hq, names = ref
+    assert mine["n"] == n
+    assert np.array_equal(mine["len"], lens)
+    assert mine["names"] == names
+    for r in range(n):
+        o, L = int(mine["off"][r]), int(lens[r])
+        assert np.array_equal(mine["codes"][o:o + L + 1], codes[r, :L + 1]), r
+        if hq:
+            assert np.array_equal(mine["qual"][o:o + L + 1], quals[r, :L + 1]), r
+        else:
+            assert mine["qual"] is None
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "gz", "no_trailing_newline", "exotic"])
+def test_reader_matches_reference_reader(tmp_path, variant):
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    recs = random_records(rng, 2500, exotic=(variant == "exotic"))
+    path = tmp_path / ("x.fq.gz" if variant == "gz" else "x.fq")
+    write_fastq(path, recs, crlf=(variant == "crlf"), trailing_newline=(variant != "no_trailing_newline"))
+    R = RefReader()
+    rd = FastqReader(path)
+    # chunk size that does not divide the file, several chunks, then end of input
+    for k in range(4):
+        mine = rd.next(1000, threads=3)
+        ref = R.chunk(path, 1000, k)
+        if ref[0] == 0:
+            assert mine is None
+            break
+        assert_chunk_equal(mine, ref)
+    rd.close()
+
+
+def test_reader_fasta_and_blank_lines(tmp_path):
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    path = tmp_path / "x.fa"
+    with open(path, "w") as fh:
+        for k in range(300):
+            fh.write(f">seq{k} d\nACGTNNACGT{'ACGT' * (k % 9)}\n")
+            if k % 10 == 0:
+                fh.write("\n")                      # blank line
+            if k % 25 == 0:
+                fh.write("GGGGGGGG\n")              # second sequence line: ignored by the reference's reader
+    R = RefReader()
+    rd = FastqReader(path)
+    assert_chunk_equal(rd.next(1000, threads=2), R.chunk(path, 1000, 0))
+    assert rd.next(1000) is None
+    rd.close()
+
+
+def test_reader_errors(tmp_path):
+    with pytest.raises(TagdustError):
+        FastqReader(tmp_path / "missing.fq")
+    p = tmp_path / "bad.fq"
+    p.write_text("@r1\nACGT\n+\nIII\n")           # io.c:1770 "Length of sequence and base qualities differ"
+    rd = FastqReader(p)
+    with pytest.raises(TagdustError) as e:
+        rd.next(10)
+    assert "differ" in str(e.value)
+    rd.close()
+    with pytest.raises(TagdustError):
+        FastqReader(tmp_path / "x.bam") if (tmp_path / "x.bam").write_text("x") else None
+
+
+def test_empty_file(tmp_path):
+    p = tmp_path / "empty.fq"
+    p.write_text("")
+    rd = FastqReader(p)
+    assert rd.next(10) is None
+    rd.close()
+
+
+def run_ref_cli(tmp, args, prefix, tag="cpu"):
+    d = os.path.join(tmp, tag)
+    os.makedirs(d, exist_ok=True)
+    r = subprocess.run(f"{REFDIR}/tagdust_rtest -seed 42 {args} -o {d}/{prefix}", cwd=tmp, shell=True, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return d
+
+
+def test_demux_read_only_architecture_matches_reference_cli(tmp_path):
+    """-1 R:N on two paired files (no HMM, no GPU): dust filter, cross-file merge of read_type,
+    READ1/READ2 + un files byte-identical to the reference CLI."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    tmp = str(tmp_path)
+    rng = np.random.default_rng(9)
+    recs1 = random_records(rng, 3000, lo=30, hi=80)
+    recs2 = []
+    for k, (n, s, q) in enumerate(recs1):
+        L = int(rng.integers(30, 81))
+        s2 = "".join(rng.choice(list("ACGT"), size=L)) if k % 17 else "A" * L      # low complexity -> read_type 6
+        recs2.append((n, s2, "".join(chr(int(c)) for c in rng.integers(33, 75, size=L))))
+    write_fastq(os.path.join(tmp, "r1.fq"), recs1)
+    write_fastq(os.path.join(tmp, "r2.fq"), recs2)
+    cpu = run_ref_cli(tmp, "-1 R:N r1.fq r2.fq", "out")
+    mine = os.path.join(tmp, "mine"); os.makedirs(mine)
+    st = demux_run(None, [dict(path=os.path.join(tmp, "r1.fq"), model=None, num_read_segments=1),
+                          dict(path=os.path.join(tmp, "r2.fq"), model=None, num_read_segments=1)],
+                   os.path.join(mine, "out"), dust=100, threads=4, chunk_reads=700)
+    a = sorted(glob.glob(os.path.join(cpu, "out*.fq"))); b = sorted(glob.glob(os.path.join(mine, "out*.fq")))
+    assert [os.path.basename(x) for x in a] == [os.path.basename(x) for x in b] and len(a) == 4
+    for x, y in zip(a, b):
+        assert filecmp.cmp(x, y, shallow=False), os.path.basename(x)
+    assert st["total_read"] == 3000
+    log = open(os.path.join(cpu, "out_logfile.txt")).read()
+    assert f"{st['num_EXTRACT_SUCCESS']}\tsuccessfully extracted" in log
+    assert f"{st['num_EXTRACT_FAIL_LOW_COMPLEXITY']}\tlow complexity" in log
+
+
+def test_demux_unequal_files_error(tmp_path):
+    rng = np.random.default_rng(1)
+    recs = random_records(rng, 50, lo=30, hi=40)
+    write_fastq(tmp_path / "a.fq", recs)
+    write_fastq(tmp_path / "b.fq", recs[:40])
+    with pytest.raises(TagdustError) as e:
+        demux_run(None, [dict(path=tmp_path / "a.fq", model=None), dict(path=tmp_path / "b.fq", model=None)], tmp_path / "o", threads=2)
+    assert "differ in number of entries" in str(e.value)
