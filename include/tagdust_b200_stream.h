@@ -53,6 +53,24 @@ int  tdg_fastq_open(const char* path, int fasta, tdg_fastq** out);
 int  tdg_fastq_next(tdg_fastq* f, int max_reads, int threads, tdg_fastq_chunk* chunk);
 void tdg_fastq_close(tdg_fastq* f);
 
+/* ---- sequence statistics (get_sequence_stats, io.c:52-300) ---------------------------------
+ * The raw sums that function accumulates over the first reads of a file: chunks of num_query
+ * reads until more than 1 000 000 have been seen (io.c:145-213).  All sums are sums of integers,
+ * so the multi-threaded accumulation is exact; the caller derives ssi->average_length,
+ * ssi->background[] and the 5'/3' partial-segment mean / stdev from them as io.c:216-270 does.
+ * five / three: nuc_code[] of the P segment at the 5' / 3' end of the architecture, or NULL. */
+typedef struct tdg_seq_stats {
+	int64_t total_read;
+	int32_t max_seq_len;
+	double  sum_len;           /* ssi->average_length before the division */
+	double  base_count[5];     /* ssi->background[] increments (without the initial 1.0) */
+	double  five_s0, five_s1, five_s2;
+	double  three_s0, three_s1, three_s2;
+} tdg_seq_stats;
+int  tdg_sequence_stats(const char* path, int fasta, int num_query,
+                        const uint8_t* five, int five_len, const uint8_t* three, int three_len,
+                        int threads, tdg_seq_stats* out);
+
 /* Append a parsed chunk (ragged rows) to a batch, packing on `threads` host threads. */
 int  tdg_batch_append_ragged(tdg_batch* b, int n, const uint8_t* codes, const uint64_t* seq_off,
                              const int32_t* len, int threads);
@@ -95,7 +113,7 @@ typedef struct tdg_demux_stats {       /* struct log_information, barcode_hmm.c:
 	int64_t num_EXTRACT_FAIL_MATCHES_ARTIFACTS;
 	int64_t num_EXTRACT_FAIL_LOW_COMPLEXITY;
 	int64_t long_sequence_events;      /* reads with len >= the running max_seq_len (:293-309: one model rebuild each) */
-	double  seconds_parse, seconds_gpu_wait, seconds_write, seconds_total;  /* busy time per stage */
+	double  seconds_split, seconds_parse, seconds_gpu_wait, seconds_write, seconds_total;  /* busy time per stage */
 } tdg_demux_stats;
 
 /* Runs the whole job; blocking.  Returns TDG_OK, or an error code with the message in the last-error string

@@ -265,8 +265,8 @@ int hmm_controller_multiple(struct parameters* param)
 		say(param, "%d	low complexity\n", (int)st.num_EXTRACT_FAIL_LOW_COMPLEXITY);
 		say(param, "%d	match artifacts:\n", (int)st.num_EXTRACT_FAIL_MATCHES_ARTIFACTS);
 		if (getenv("TDG_VERBOSE"))
-			fprintf(stderr, "tagdust_b200: %lld reads in %.2f s (parse %.2f s, gpu wait %.2f s, write %.2f s busy)\n",
-			        (long long)st.total_read, st.seconds_total, st.seconds_parse, st.seconds_gpu_wait, st.seconds_write);
+			fprintf(stderr, "tagdust_b200: %lld reads in %.2f s (busy: line split %.2f s, convert+pack %.2f s, gpu wait %.2f s, write %.2f s)\n",
+			        (long long)st.total_read, st.seconds_total, st.seconds_split, st.seconds_parse, st.seconds_gpu_wait, st.seconds_write);
 	}
 
 DONE:

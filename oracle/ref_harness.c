@@ -425,3 +425,28 @@ int refh_read_file_chunk(const char* path, int num_query, int chunk_index, int s
 	free(param);
 	return numseq;
 }
+
+/* ---------------- get_sequence_stats (io.c:52-300) through the reference's own function ----------------
+ * out[0..4] background, [5] expected_5, [6] expected_3, [7] mean_5, [8] stdev_5, [9] mean_3, [10] stdev_3,
+ * [11] average_length, [12] max_seq_len */
+int refh_sequence_stats(struct parameters* param, const char* path, int num_query, double* out)
+{
+	struct read_info** ri = NULL;
+	struct sequence_stats_info* ssi;
+	char* files[1];
+	char** keep_files = param->infile;
+	int keep_n = param->infiles, keep_q = param->num_query, i;
+	files[0] = (char*)path;
+	param->infile = files; param->infiles = 1; param->num_query = num_query;
+	ri = malloc_read_info(ri, num_query);
+	ssi = get_sequence_stats(param, ri, 0);
+	free_read_info(ri, num_query);
+	param->infile = keep_files; param->infiles = keep_n; param->num_query = keep_q;
+	if(!ssi) return -1;
+	for(i = 0; i < 5; i++) out[i] = ssi->background[i];
+	out[5] = ssi->expected_5_len; out[6] = ssi->expected_3_len;
+	out[7] = ssi->mean_5_len; out[8] = ssi->stdev_5_len; out[9] = ssi->mean_3_len; out[10] = ssi->stdev_3_len;
+	out[11] = ssi->average_length; out[12] = ssi->max_seq_len;
+	free(ssi);
+	return 0;
+}

@@ -13,15 +13,16 @@ ls -la $W/syn48.fq; nproc
 ARCH=$W/syn48.fq_tagdust_arch.txt
 # (1) throughput of the whole tool, fixed threshold (no calibration phase) and with calibration
 for Q in "-Q 1.5" ""; do
-  /usr/bin/time -f "wall %e s  user %U  sys %S  maxrss %M KB" timeout 600 env TDG_VERBOSE=1 integration/_build/tagdust_gpu -t $(nproc) $Q -arch $ARCH $W/syn48.fq -o $W/gpu_full > $W/full.log 2>&1
-  echo "rc=$? Q='$Q'"; tail -4 $W/full.log; grep -E "total input|extracted|Threshold|threshold" $W/gpu_full_logfile.txt
+  T0=$(date +%s.%N)
+  timeout 600 env TDG_VERBOSE=1 integration/_build/tagdust_gpu -t $(nproc) $Q -arch $ARCH $W/syn48.fq -o $W/gpu_full > $W/full.log 2>&1
+  echo "rc=$? Q='$Q' wall $(python3 -c "import time,sys; print(round(time.time()-float(sys.argv[1]),2))" $T0) s for $N reads"; tail -4 $W/full.log; grep -E "total input|extracted|Threshold|threshold" $W/gpu_full_logfile.txt
   rm -f $W/gpu_full*
 done
 # (2) byte comparison with the CPU reference on a prefix
 head -n $((NCMP*4)) $W/syn48.fq > $W/small.fq
 mkdir -p $W/cpu $W/gpu
-/usr/bin/time -f "cpu reference wall %e s" timeout 900 $REF/tagdust -t $(nproc) -Q 1.5 -arch $ARCH $W/small.fq -o $W/cpu/out > /dev/null 2>&1; echo rc=$?
-/usr/bin/time -f "gpu drop-in wall %e s" timeout 300 integration/_build/tagdust_gpu -t $(nproc) -Q 1.5 -arch $ARCH $W/small.fq -o $W/gpu/out > /dev/null 2>&1; echo rc=$?
+T0=$(date +%s.%N); timeout 900 $REF/tagdust -t $(nproc) -Q 1.5 -arch $ARCH $W/small.fq -o $W/cpu/out > /dev/null 2>&1; echo "rc=$? cpu reference wall $(python3 -c "import time,sys; print(round(time.time()-float(sys.argv[1]),2))" $T0) s for $NCMP reads"
+T0=$(date +%s.%N); timeout 300 integration/_build/tagdust_gpu -t $(nproc) -Q 1.5 -arch $ARCH $W/small.fq -o $W/gpu/out > /dev/null 2>&1; echo "rc=$? gpu drop-in wall $(python3 -c "import time,sys; print(round(time.time()-float(sys.argv[1]),2))" $T0) s for $NCMP reads"
 nd=0; for f in $W/cpu/*.fq; do cmp -s $f $W/gpu/$(basename $f) || { echo DIFF $(basename $f); nd=$((nd+1)); }; done
 echo "files compared: $(ls $W/cpu/*.fq | wc -l), differing: $nd"
 grep -E "total input|successfully" $W/cpu/out_logfile.txt $W/gpu/out_logfile.txt

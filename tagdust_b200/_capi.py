@@ -178,11 +178,18 @@ class DemuxStatsC(C.Structure):
         "total_read", "num_EXTRACT_SUCCESS", "num_EXTRACT_FAIL_BAR_FINGER_NOT_FOUND", "num_EXTRACT_FAIL_READ_TOO_SHORT",
         "num_EXTRACT_FAIL_AMBIGIOUS_BARCODE", "num_EXTRACT_FAIL_ARCHITECTURE_MISMATCH", "num_EXTRACT_FAIL_MATCHES_ARTIFACTS",
         "num_EXTRACT_FAIL_LOW_COMPLEXITY", "long_sequence_events")] + [(k, C.c_double) for k in (
-            "seconds_parse", "seconds_gpu_wait", "seconds_write", "seconds_total")]
+            "seconds_split", "seconds_parse", "seconds_gpu_wait", "seconds_write", "seconds_total")]
+
+
+class SeqStatsC(C.Structure):
+    _fields_ = [("total_read", C.c_int64), ("max_seq_len", C.c_int32), ("sum_len", C.c_double), ("base_count", C.c_double * 5),
+                ("five_s0", C.c_double), ("five_s1", C.c_double), ("five_s2", C.c_double),
+                ("three_s0", C.c_double), ("three_s1", C.c_double), ("three_s2", C.c_double)]
 
 
 #: every symbol include/tagdust_b200_stream.h declares
 STREAM_PROTOTYPES = {
+    "tdg_sequence_stats": (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_uint8_p, C.c_int, c_uint8_p, C.c_int, C.c_int, C.POINTER(SeqStatsC)]),
     "tdg_fastq_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "tdg_fastq_next": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(FastqChunkC)]),
     "tdg_fastq_close": (None, [C.c_void_p]),

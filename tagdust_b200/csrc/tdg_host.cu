@@ -447,6 +447,7 @@ struct Shard {  // one device's part of a batch
 	cudaStream_t copy = nullptr;
 	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 	int cap = 0;  // reads of device capacity
+	void* slab = nullptr;  // one device allocation behind all the arrays below
 	uint32_t* seq = nullptr; int32_t* len = nullptr;
 	float *mapq = nullptr, *bar_prob = nullptr, *f = nullptr, *b = nullptr, *r = nullptr;
 	int32_t *read_type = nullptr, *barcode = nullptr, *fingerprint = nullptr;
@@ -456,13 +457,19 @@ struct Shard {  // one device's part of a batch
 struct tdg_batch {
 	tdg_context* ctx = nullptr;
 	int max_reads = 0, max_len = 0, words = 0, label_stride = 0, n = 0;
-	// pinned host staging
+	// pinned host staging: one allocation (pinning is the slow part of creating a batch), carved into the arrays below
+	void* h_slab = nullptr;
 	uint32_t* h_seq = nullptr; int32_t* h_len = nullptr;
 	float *h_mapq = nullptr, *h_bar_prob = nullptr, *h_f = nullptr, *h_b = nullptr, *h_r = nullptr;
 	int32_t *h_read_type = nullptr, *h_barcode = nullptr, *h_fingerprint = nullptr;
 	uint8_t *h_extracted = nullptr, *h_labels = nullptr;
 	std::vector<Shard> shard;
 	int pending_mode = 0; bool pending = false, want_labels = false;
+};
+
+struct Carver {  // 256-byte aligned offsets into one slab
+	size_t total = 0;
+	size_t take(size_t bytes) { const size_t o = total; total += (std::max<size_t>(bytes, 1) + 255) / 256 * 256; return o; }
 };
 
 template <class T>
@@ -478,16 +485,13 @@ extern "C" void tdg_batch_destroy(tdg_batch* b)
 		cudaSetDevice(b->ctx->devs[k].dev);
 		if (s.copy) cudaStreamSynchronize(s.copy);
 		cudaStreamSynchronize(b->ctx->devs[k].compute);
-		cudaFree(s.seq); cudaFree(s.len); cudaFree(s.mapq); cudaFree(s.bar_prob); cudaFree(s.f); cudaFree(s.b); cudaFree(s.r);
-		cudaFree(s.read_type); cudaFree(s.barcode); cudaFree(s.fingerprint); cudaFree(s.extracted); cudaFree(s.labels);
+		cudaFree(s.slab);
 		if (s.h2d_done) cudaEventDestroy(s.h2d_done);
 		if (s.k_done) cudaEventDestroy(s.k_done);
 		if (s.d2h_done) cudaEventDestroy(s.d2h_done);
 		if (s.copy) cudaStreamDestroy(s.copy);
 	}
-	cudaFreeHost(b->h_seq); cudaFreeHost(b->h_len); cudaFreeHost(b->h_mapq); cudaFreeHost(b->h_bar_prob); cudaFreeHost(b->h_f);
-	cudaFreeHost(b->h_b); cudaFreeHost(b->h_r); cudaFreeHost(b->h_read_type); cudaFreeHost(b->h_barcode);
-	cudaFreeHost(b->h_fingerprint); cudaFreeHost(b->h_extracted); cudaFreeHost(b->h_labels);
+	cudaFreeHost(b->h_slab);
 	delete b;
 }
 
@@ -504,12 +508,18 @@ extern "C" int tdg_batch_create(tdg_context* ctx, int max_reads, int max_len, td
 	b->label_stride = (max_len + 1 + 7) / 8 * 8;
 	const size_t N = b->max_reads;
 	int rc;
-	if ((rc = pinned(&b->h_seq, N * b->words)) || (rc = pinned(&b->h_len, N)) || (rc = pinned(&b->h_mapq, N)) ||
-	    (rc = pinned(&b->h_bar_prob, N)) || (rc = pinned(&b->h_f, N)) || (rc = pinned(&b->h_b, N)) || (rc = pinned(&b->h_r, N)) ||
-	    (rc = pinned(&b->h_read_type, N)) || (rc = pinned(&b->h_barcode, N)) || (rc = pinned(&b->h_fingerprint, N)) ||
-	    (rc = pinned(&b->h_extracted, N)) || (rc = pinned(&b->h_labels, N * b->label_stride))) {
-		tdg_batch_destroy(b);
-		return rc;
+	{
+		Carver cv;
+		const size_t o_seq = cv.take(N * b->words * 4), o_len = cv.take(N * 4), o_mapq = cv.take(N * 4), o_bp = cv.take(N * 4),
+		             o_f = cv.take(N * 4), o_b = cv.take(N * 4), o_r = cv.take(N * 4), o_rt = cv.take(N * 4), o_bc = cv.take(N * 4),
+		             o_fp = cv.take(N * 4), o_ex = cv.take(N), o_lab = cv.take(N * b->label_stride);
+		char* base = nullptr;
+		if ((rc = pinned(&base, cv.total))) { tdg_batch_destroy(b); return rc; }
+		b->h_slab = base;
+		b->h_seq = (uint32_t*)(base + o_seq); b->h_len = (int32_t*)(base + o_len); b->h_mapq = (float*)(base + o_mapq);
+		b->h_bar_prob = (float*)(base + o_bp); b->h_f = (float*)(base + o_f); b->h_b = (float*)(base + o_b); b->h_r = (float*)(base + o_r);
+		b->h_read_type = (int32_t*)(base + o_rt); b->h_barcode = (int32_t*)(base + o_bc); b->h_fingerprint = (int32_t*)(base + o_fp);
+		b->h_extracted = (uint8_t*)(base + o_ex); b->h_labels = (uint8_t*)(base + o_lab);
 	}
 	memset(b->h_seq, 0, N * b->words * 4);
 	const int nd = (int)ctx->devs.size();
@@ -521,12 +531,18 @@ extern "C" int tdg_batch_create(tdg_context* ctx, int max_reads, int max_len, td
 		cudaSetDevice(ctx->devs[k].dev);
 		s.cap = per;
 		const size_t P = per;
-		if ((rc = devalloc(&s.seq, P * b->words)) || (rc = devalloc(&s.len, P)) || (rc = devalloc(&s.mapq, P)) ||
-		    (rc = devalloc(&s.bar_prob, P)) || (rc = devalloc(&s.f, P)) || (rc = devalloc(&s.b, P)) || (rc = devalloc(&s.r, P)) ||
-		    (rc = devalloc(&s.read_type, P)) || (rc = devalloc(&s.barcode, P)) || (rc = devalloc(&s.fingerprint, P)) ||
-		    (rc = devalloc(&s.extracted, P)) || (rc = devalloc(&s.labels, P * b->label_stride))) {
-			tdg_batch_destroy(b);
-			return rc;
+		{
+			Carver cv;
+			const size_t o_seq = cv.take(P * b->words * 4), o_len = cv.take(P * 4), o_mapq = cv.take(P * 4), o_bp = cv.take(P * 4),
+			             o_f = cv.take(P * 4), o_b = cv.take(P * 4), o_r = cv.take(P * 4), o_rt = cv.take(P * 4), o_bc = cv.take(P * 4),
+			             o_fp = cv.take(P * 4), o_ex = cv.take(P), o_lab = cv.take(P * b->label_stride);
+			char* base = nullptr;
+			if ((rc = devalloc(&base, cv.total))) { tdg_batch_destroy(b); return rc; }
+			s.slab = base;
+			s.seq = (uint32_t*)(base + o_seq); s.len = (int32_t*)(base + o_len); s.mapq = (float*)(base + o_mapq);
+			s.bar_prob = (float*)(base + o_bp); s.f = (float*)(base + o_f); s.b = (float*)(base + o_b); s.r = (float*)(base + o_r);
+			s.read_type = (int32_t*)(base + o_rt); s.barcode = (int32_t*)(base + o_bc); s.fingerprint = (int32_t*)(base + o_fp);
+			s.extracted = (uint8_t*)(base + o_ex); s.labels = (uint8_t*)(base + o_lab);
 		}
 		if (cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -682,10 +698,23 @@ static void fill_model_args(KArgs& a, const tdg_model* m, int devk, const Device
 	a.required_finger_len = hm.required_finger_len;
 }
 
-static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool full)
+// CTAs (of kBlock reads) per wave: one per SM, fewer when the per-read scratch of a long-read model
+// (threshold calibration emits reads several times the average length) would not fit in HBM.
+static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full)
+{
+	size_t free_b = 0, total_b = 0;
+	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return d.ctas; }
+	const double budget = 0.90 * (double)(free_b + d.scratch_bytes);
+	const double per_cta = (double)kBlock * (double)(full ? m->slot_bytes_full : m->slot_bytes_bwd);
+	long fit = (long)(budget / per_cta);
+	if (fit < 1) fit = 1;
+	return (int)std::min<long>(d.ctas, fit);
+}
+
+static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool full, int wave_ctas)
 {
 	const HostModel& hm = m->hm;
-	const size_t slots = (size_t)d.ctas * kBlock;
+	const size_t slots = (size_t)wave_ctas * kBlock;
 	const size_t W = (size_t)m->max_len + 2;
 	char* p = (char*)d.scratch;
 	auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) / 256 * 256; return q; };
@@ -700,15 +729,15 @@ static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool
 	}
 }
 
-static size_t scratch_need(const tdg_model* m, const DeviceCtx& d, bool full)
+static size_t scratch_need(const tdg_model* m, bool full, int wave_ctas)
 {
-	const size_t slots = (size_t)d.ctas * kBlock;
+	const size_t slots = (size_t)wave_ctas * kBlock;
 	return slots * (full ? m->slot_bytes_full : m->slot_bytes_bwd) + 10 * 256;
 }
 
 // Queue all waves of one shard on `stream`.  Returns kernel launches queued (<0 on error).
 static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_params* p, tdg_batch* b, int devk,
-                        cudaStream_t stream, float* b_score_override)
+                        cudaStream_t stream, float* b_score_override, int wave_ctas)
 {
 	DeviceCtx& d = ctx->devs[devk];
 	Shard& s = b->shard[devk];
@@ -717,7 +746,7 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	const bool want_labels = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p && p->want_labels);
 	KArgs a;
 	fill_model_args(a, m, devk, d);
-	carve_scratch(a, m, d, !bwd_only);
+	carve_scratch(a, m, d, !bwd_only, wave_ctas);
 	a.words = b->words;
 	a.win_start = 0; a.win_len = -1;
 	if (p && (p->matchstart != -1 || p->matchend != -1)) { a.win_start = p->matchstart; a.win_len = p->matchend - p->matchstart; }
@@ -727,7 +756,7 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	a.dust = (p && mode == TDG_MODE_GET_LABEL) ? p->dust : 0;
 	a.do_extract = (mode == TDG_MODE_GET_LABEL);
 	a.want_labels = want_labels;
-	const int wave = d.ctas * kBlock;
+	const int wave = wave_ctas * kBlock;
 	int launches = 0;
 	for (int w0 = 0; w0 < s.n; w0 += wave) {
 		const int nw = std::min(wave, s.n - w0);
@@ -836,11 +865,12 @@ extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_ru
 		Shard& s = b->shard[k];
 		if (s.n == 0) continue;
 		CK(cudaSetDevice(d.dev));
-		if ((rc = ensure_scratch(d, scratch_need(m, d, mode != TDG_MODE_ARCH_COMP)))) return rc;
+		const int wc = plan_wave_ctas(m, d, mode != TDG_MODE_ARCH_COMP);
+		if ((rc = ensure_scratch(d, scratch_need(m, mode != TDG_MODE_ARCH_COMP, wc)))) return rc;
 		if ((rc = upload_shard(b, (int)k, s.copy))) return rc;
 		CK(cudaEventRecord(s.h2d_done, s.copy));
 		CK(cudaStreamWaitEvent(d.compute, s.h2d_done, 0));
-		if (queue_decode(ctx, m, mode, p, b, (int)k, d.compute, nullptr) < 0) return TDG_ECUDA;
+		if (queue_decode(ctx, m, mode, p, b, (int)k, d.compute, nullptr, wc) < 0) return TDG_ECUDA;
 		CK(cudaEventRecord(s.k_done, d.compute));
 		CK(cudaStreamWaitEvent(s.copy, s.k_done, 0));
 		if ((rc = download_shard(b, (int)k, s.copy, mode, want_labels))) return rc;
@@ -930,10 +960,11 @@ extern "C" int tdg_decode_resident(tdg_context* ctx, tdg_model* m, int mode, con
 		DeviceCtx& d = ctx->devs[k];
 		if (b->shard[k].n == 0) continue;
 		CK(cudaSetDevice(d.dev));
-		if ((rc = ensure_scratch(d, scratch_need(m, d, mode != TDG_MODE_ARCH_COMP)))) return rc;
+		const int wc = plan_wave_ctas(m, d, mode != TDG_MODE_ARCH_COMP);
+		if ((rc = ensure_scratch(d, scratch_need(m, mode != TDG_MODE_ARCH_COMP, wc)))) return rc;
 		// a caller-provided stream is only meaningful for a single-device context
 		cudaStream_t st = (ctx->devs.size() == 1) ? (cudaStream_t)cuda_stream : d.compute;
-		const int l = queue_decode(ctx, m, mode, p, b, (int)k, st, nullptr);
+		const int l = queue_decode(ctx, m, mode, p, b, (int)k, st, nullptr, wc);
 		if (l < 0) return TDG_ECUDA;
 		total += l;
 	}

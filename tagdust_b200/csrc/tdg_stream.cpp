@@ -103,16 +103,52 @@ bool has_suffix(const std::string& s, const char* suf)
 // ------------------------------------------------------------------------------------------
 // parsed chunk storage
 // ------------------------------------------------------------------------------------------
+// Growable POD array without value-initialisation: a std::vector would memset hundreds of MB on one
+// thread (and take all the first-touch page faults there) every time a chunk buffer grows.
+template <class T>
+struct RawVec {
+	T* p = nullptr;
+	size_t n = 0, cap = 0;
+	RawVec() = default;
+	RawVec(const RawVec&) = delete;
+	RawVec& operator=(const RawVec&) = delete;
+	RawVec(RawVec&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+	~RawVec() { free(p); }
+	void reserve(size_t want)
+	{
+		if (want <= cap) return;
+		size_t nc = std::max(want, cap + cap / 2 + 64);
+		T* q = (T*)realloc(p, nc * sizeof(T));
+		if (!q) throw std::bad_alloc();
+		p = q; cap = nc;
+	}
+	void resize(size_t m) { reserve(m); n = m; }
+	void clear() { n = 0; }
+	void push_back(const T& v) { if (n == cap) reserve(n + 1); p[n++] = v; }
+	bool empty() const { return n == 0; }
+	size_t size() const { return n; }
+	T* data() { return p; }
+	const T* data() const { return p; }
+	T& operator[](size_t i) { return p[i]; }
+	const T& operator[](size_t i) const { return p[i]; }
+	T& back() { return p[n - 1]; }
+};
+
 struct ParsedChunk {
 	int n = 0, max_len = 0;
 	bool fasta = false;
-	std::vector<int32_t> len;
-	std::vector<uint64_t> seq_off, name_off;
-	std::vector<uint8_t> codes, qual;
-	std::vector<char> names;
-	// line table of the sequential pass: offsets into the reader's text, piece lengths (without the newline)
+	RawVec<int32_t> len;
+	RawVec<uint64_t> seq_off, name_off;
+	RawVec<uint8_t> codes, qual;
+	RawVec<char> names;
+	// line table of the sequential pass: offsets into `text`, piece lengths (without the newline)
 	struct Rec { uint64_t name, seq, qual; uint32_t name_n, seq_n, qual_n; uint8_t has_seq, has_qual; };
-	std::vector<Rec> recs;
+	RawVec<Rec> recs;
+	// the text the line table points into: the reader's mapping (plain files) or a buffer owned by
+	// this chunk (pipes), so that the line pass of the next chunk can run while this one is converted
+	const char* text = nullptr;
+	RawVec<char> own_text;
+	std::string path;
 };
 
 struct tdg_fastq {
@@ -121,25 +157,26 @@ struct tdg_fastq {
 	// plain file: mmap; pipe: growing buffer
 	const char* map = nullptr; size_t map_len = 0; int fd = -1;
 	FILE* pipe = nullptr;
-	std::vector<char> buf;
-	size_t beg = 0, end = 0;   // unconsumed text [beg, end) of `text()`
+	RawVec<char> carry;        // pipe: bytes read but not consumed by the previous chunk
+	size_t beg = 0, end = 0;   // plain file: unconsumed part [beg, end) of the mapping
 	bool eof = false;
 	int set = 0, seq_p = 0;    // read_fasta_fastq's flags; they persist across chunks like the FILE position does
 	ParsedChunk own;           // storage behind the public tdg_fastq_next
-	const char* text() const { return map ? map : buf.data(); }
 };
 
-static int reader_fill(tdg_fastq* f)
+// pipe only: append another block to the chunk's own text; returns bytes added (0 at end of input)
+static int reader_fill(tdg_fastq* f, ParsedChunk& pc, size_t* added)
 {
-	// pipe only: append another block after `end`
-	const size_t block = (size_t)16 << 20;
-	if (f->buf.size() < f->end + block) f->buf.resize(std::max(f->buf.size() * 2, f->end + block));
-	const size_t got = fread(f->buf.data() + f->end, 1, block, f->pipe);
+	const size_t block = (size_t)8 << 20;
+	const size_t have = pc.own_text.size();
+	pc.own_text.reserve(have + block);
+	const size_t got = fread(pc.own_text.data() + have, 1, block, f->pipe);
 	if (got == 0) {
 		if (ferror(f->pipe)) return failf(TDG_EIO, "read error on %s", f->path.c_str());
 		f->eof = true;
 	}
-	f->end += got;
+	pc.own_text.n = have + got;
+	*added = got;
 	return TDG_OK;
 }
 
@@ -196,26 +233,38 @@ extern "C" void tdg_fastq_close(tdg_fastq* f)
 }
 
 // Sequential pass: split lines, run read_fasta_fastq's state machine, fill pc.recs.
-// Conversion pass: names, codes, qualities on the worker pool.
-static int parse_next(tdg_fastq* f, int max_reads, int threads, ParsedChunk& pc)
+static int split_lines(tdg_fastq* f, int max_reads, ParsedChunk& pc)
 {
-	pc.n = 0; pc.max_len = 0; pc.fasta = f->fasta;
+	pc.n = 0; pc.max_len = 0; pc.fasta = f->fasta; pc.path = f->path;
 	pc.recs.clear();
 	if (max_reads < 1) return failf(TDG_EINVAL, "max_reads must be >= 1");
-	if (f->pipe && f->beg > 0) {  // compact the unconsumed tail to the front
-		memmove(f->buf.data(), f->buf.data() + f->beg, f->end - f->beg);
-		f->end -= f->beg; f->beg = 0;
+	size_t pos, end;
+	if (f->pipe) {  // start from what the previous chunk left over
+		pc.own_text.clear();
+		pc.own_text.reserve(f->carry.size() + 1);
+		if (f->carry.size()) memcpy(pc.own_text.data(), f->carry.data(), f->carry.size());
+		pc.own_text.n = f->carry.size();
+		f->carry.clear();
+		pos = 0; end = pc.own_text.size();
+	} else {
+		pc.text = f->map;
+		pos = f->beg; end = f->end;
 	}
-	size_t pos = f->beg;
 	bool done = false;
 	while (!done) {
-		const char* base = f->text();
-		const char* nl = (pos < f->end) ? (const char*)memchr(base + pos, '\n', std::min(f->end - pos, (size_t)kMaxLine - 1)) : nullptr;
+		const char* base = f->pipe ? pc.own_text.data() : f->map;
+		const char* nl = (pos < end) ? (const char*)memchr(base + pos, '\n', std::min(end - pos, (size_t)kMaxLine - 1)) : nullptr;
 		size_t piece, next;
 		if (nl) { piece = (size_t)(nl - (base + pos)); next = pos + piece + 1; }
-		else if (f->end - pos >= (size_t)kMaxLine - 1) { piece = kMaxLine - 1; next = pos + piece; }  // fgets() splits long lines
-		else if (!f->eof) { int rc = reader_fill(f); if (rc) return rc; continue; }
-		else if (pos < f->end) { piece = f->end - pos; next = f->end; }  // last line without newline
+		else if (end - pos >= (size_t)kMaxLine - 1) { piece = kMaxLine - 1; next = pos + piece; }  // fgets() splits long lines
+		else if (!f->eof) {
+			size_t added = 0;
+			int rc = reader_fill(f, pc, &added);
+			if (rc) return rc;
+			end = pc.own_text.size();
+			continue;
+		}
+		else if (pos < end) { piece = end - pos; next = end; }  // last line without newline
 		else break;
 		const char c0 = piece ? base[pos] : '\n';
 		if ((c0 == '@' || c0 == '>') && !f->set) {
@@ -240,17 +289,32 @@ static int parse_next(tdg_fastq* f, int max_reads, int threads, ParsedChunk& pc)
 			if ((!f->fasta && r.has_qual) || (f->fasta && r.has_seq)) done = true;
 		}
 	}
-	f->beg = pos;
-	const int n = (int)pc.recs.size();
-	pc.n = n;
+	if (f->pipe) {
+		pc.text = pc.own_text.data();
+		f->carry.resize(end - pos);
+		if (end > pos) memcpy(f->carry.data(), pc.own_text.data() + pos, end - pos);
+	} else {
+		f->beg = pos;
+	}
+	pc.n = (int)pc.recs.size();
+	return TDG_OK;
+}
+
+// Conversion pass: names, codes, qualities on the worker pool.
+static int convert_chunk(ParsedChunk& pc, int threads)
+{
+	struct { const char* path; bool fasta; } fv = {pc.path.c_str(), pc.fasta};
+	auto* f = &fv;
+	const double tt1 = now_s();
+	const int n = pc.n;
 	if (n == 0) return TDG_OK;
 	// offsets (upper bounds: the piece lengths; the real lengths stop at the first control character)
 	pc.len.resize(n); pc.seq_off.resize(n); pc.name_off.resize((size_t)n + 1);
 	uint64_t so = 0, no = 0;
 	for (int r = 0; r < n; r++) {
 		const ParsedChunk::Rec& R = pc.recs[r];
-		if (!R.has_seq) return failf(TDG_EFORMAT, "%s: entry %d has no sequence line", f->path.c_str(), r);
-		if (!f->fasta && !R.has_qual) return failf(TDG_EFORMAT, "%s: entry %d has no quality line", f->path.c_str(), r);
+		if (!R.has_seq) return failf(TDG_EFORMAT, "%s: entry %d has no sequence line", f->path, r);
+		if (!f->fasta && !R.has_qual) return failf(TDG_EFORMAT, "%s: entry %d has no quality line", f->path, r);
 		pc.seq_off[r] = so; so += (uint64_t)R.seq_n + 1;
 		pc.name_off[r] = no; no += (uint64_t)R.name_n;  // '@' dropped, NUL added
 	}
@@ -258,7 +322,7 @@ static int parse_next(tdg_fastq* f, int max_reads, int threads, ParsedChunk& pc)
 	pc.codes.resize(so);
 	if (!f->fasta) pc.qual.resize(so); else pc.qual.clear();
 	pc.names.resize(no);
-	const char* base = f->text();
+	const char* base = pc.text;
 	std::atomic<int> bad{-1};
 	std::vector<int> tmax((size_t)std::max(1, threads), 0);
 	const bool fasta = f->fasta;
@@ -293,6 +357,7 @@ static int parse_next(tdg_fastq* f, int max_reads, int threads, ParsedChunk& pc)
 		}
 		tmax[t] = std::max(tmax[t], mx);
 	});
+	if (getenv("TDG_TRACE")) fprintf(stderr, "convert_chunk: %d reads, %.3f s\n", n, now_s() - tt1);
 	if (bad.load() >= 0) return failf(TDG_EFORMAT, "ERROR: Length of sequence and base qualities differ!.");  // io.c:1770
 	for (int v : tmax) pc.max_len = std::max(pc.max_len, v);
 	return TDG_OK;
@@ -301,7 +366,8 @@ static int parse_next(tdg_fastq* f, int max_reads, int threads, ParsedChunk& pc)
 extern "C" int tdg_fastq_next(tdg_fastq* f, int max_reads, int threads, tdg_fastq_chunk* chunk)
 {
 	if (!f || !chunk) return failf(TDG_EINVAL, "tdg_fastq_next: NULL argument");
-	int rc = parse_next(f, max_reads, threads, f->own);
+	int rc = split_lines(f, max_reads, f->own);
+	if (!rc) rc = convert_chunk(f->own, threads);
 	memset(chunk, 0, sizeof *chunk);
 	if (rc) return rc;
 	const ParsedChunk& pc = f->own;
@@ -312,6 +378,70 @@ extern "C" int tdg_fastq_next(tdg_fastq* f, int max_reads, int threads, tdg_fast
 		chunk->name_off = pc.name_off.data(); chunk->names = pc.names.data();
 	}
 	return TDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// get_sequence_stats (io.c:52-300): raw sums over the first reads of a file
+// ------------------------------------------------------------------------------------------
+extern "C" int tdg_sequence_stats(const char* path, int fasta, int num_query, const uint8_t* five, int five_len,
+                                  const uint8_t* three, int three_len, int threads, tdg_seq_stats* out)
+{
+	if (!path || !out || num_query < 1) return failf(TDG_EINVAL, "tdg_sequence_stats: bad argument");
+	memset(out, 0, sizeof *out);
+	tdg_fastq* f = nullptr;
+	int rc = tdg_fastq_open(path, fasta, &f);
+	if (rc) return rc;
+	const int T = std::max(1, threads);
+	struct Acc { int64_t n_len = 0, base[5] = {0, 0, 0, 0, 0}, f0 = 0, f1 = 0, f2 = 0, t0 = 0, t1 = 0, t2 = 0; int mx = 0; };
+	ParsedChunk& pc = f->own;
+	// the reference reads whole chunks of num_query reads until more than 1 000 000 have been seen (io.c:145-213)
+	const int64_t target = ((int64_t)1000000 / num_query + 1) * (int64_t)num_query;
+	while (out->total_read < target) {
+		const int want = (int)std::min<int64_t>(target - out->total_read, (int64_t)1 << 20);
+		if ((rc = split_lines(f, want, pc)) || (rc = convert_chunk(pc, T))) break;
+		if (pc.n == 0) break;
+		std::vector<Acc> acc((size_t)T);
+		const uint8_t* end_of_codes = pc.codes.data() + pc.codes.size();
+		parallel_for(T, (size_t)pc.n, 4096, [&](size_t b, size_t e, int t) {
+			Acc a;
+			for (size_t r = b; r < e; r++) {
+				const uint8_t* seq = pc.codes.data() + pc.seq_off[r];
+				const int len = pc.len[r];
+				if (len > a.mx) a.mx = len;
+				a.n_len += len;
+				for (int j = 0; j < len; j++) if (seq[j] < 5) a.base[seq[j]]++;
+				if (five_len) {  // longest exact match of a suffix of the 5' partial segment with the read start (io.c:160-175)
+					for (int j = 0; j <= five_len; j++) {
+						int c;
+						for (c = 0; c < five_len - j; c++)
+							if (seq + c >= end_of_codes || seq[c] != five[j + c]) break;
+						if (c == five_len - j && c > 3) { a.f0++; a.f1 += five_len - j; a.f2 += (int64_t)(five_len - j) * (five_len - j); break; }
+					}
+				}
+				if (three_len) {  // prefix of the 3' partial segment at the read end (io.c:177-193)
+					for (int j = 0; j <= three_len; j++) {
+						int c;
+						for (c = 0; c < three_len - j; c++) {
+							const int idx = len - (three_len - j - c);
+							if (idx < 0 || seq[idx] != three[c]) break;
+						}
+						if (c == three_len - j && c > 3) { a.t0++; a.t1 += three_len - j; a.t2 += (int64_t)(three_len - j) * (three_len - j); break; }
+					}
+				}
+			}
+			acc[t] = a;
+		});
+		for (const Acc& a : acc) {
+			out->max_seq_len = std::max(out->max_seq_len, a.mx);
+			out->sum_len += (double)a.n_len;
+			for (int k = 0; k < 5; k++) out->base_count[k] += (double)a.base[k];
+			out->five_s0 += (double)a.f0; out->five_s1 += (double)a.f1; out->five_s2 += (double)a.f2;
+			out->three_s0 += (double)a.t0; out->three_s1 += (double)a.t1; out->three_s2 += (double)a.t2;
+		}
+		out->total_read += pc.n;
+	}
+	tdg_fastq_close(f);
+	return rc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -442,7 +572,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	for (int i = 0; i < NI; i++) any_model |= job->inputs[i].model != nullptr;
 	if (any_model && !ctx) return failf(TDG_EINVAL, "tdg_demux_run: a GPU context is required");
 	const int threads = std::max(1, job->threads);
-	const int chunk_reads = job->chunk_reads > 0 ? job->chunk_reads : 4 * 148 * 512;
+	const int chunk_reads = job->chunk_reads > 0 ? job->chunk_reads : 2 * 148 * 512;
 	const int nalt = job->num_alternatives;
 	if (nalt < 2) return failf(TDG_EINVAL, "num_alternatives must be >= 2");
 	const double t_start = now_s();
@@ -495,29 +625,41 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			tdg_model_read_hmms(job->inputs[i].model, is_read[i].data());
 		}
 
-	constexpr int NSLOT = 4;
+	constexpr int NSLOT = 3;
 	std::vector<Slot> slots(NSLOT);
 	for (auto& s : slots) { s.pc.resize(NI); s.batch.assign(NI, nullptr); s.batch_reads.assign(NI, 0); s.batch_len.assign(NI, 0); s.res.resize(NI); }
-	Queue<int> q_free, q_gpu, q_write;
+	Queue<int> q_free, q_conv, q_gpu, q_write;
 	for (int k = 0; k < NSLOT; k++) q_free.push(k);
 	Shared sh;
+	// pinned staging is slow to create: make all slots' batches at once, on their own threads, while
+	// the first chunk is being split (a longer read later on re-creates the batch of that slot)
+	std::vector<std::thread> t_alloc;
+	for (int k = 0; k < NSLOT; k++)
+		for (int i = 0; i < NI; i++)
+			if (job->inputs[i].model && job->inputs[i].max_seq_len > 0)
+				t_alloc.emplace_back([&, k, i] {
+					Slot& s = slots[k];
+					s.batch_reads[i] = std::min(chunk_reads, 1 << 24);
+					s.batch_len[i] = job->inputs[i].max_seq_len;
+					if (tdg_batch_create(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
+				});
+	const bool trace = getenv("TDG_TRACE") != nullptr;
+	auto tr = [&](const char* stage, int k, double t0) {
+		if (trace) fprintf(stderr, "[trace] %-8s chunk-slot %d  %.3f -> %.3f s\n", stage, k, t0 - t_start, now_s() - t_start);
+	};
 	std::atomic<int64_t> long_events{0};
-	double sec_parse = 0, sec_gpu = 0, sec_write = 0;
+	double sec_split = 0, sec_parse = 0, sec_gpu = 0, sec_write = 0;
 
-	// ---- stage 1: parse + pack
-	std::thread t_parse([&] {
-		std::vector<int> run_max(NI);
-		for (int i = 0; i < NI; i++) run_max[i] = job->inputs[i].max_seq_len;
+	// ---- stage 1a: line splitting (sequential per file)
+	std::thread t_split([&] {
 		for (;;) {
 			int k;
 			if (!q_free.pop(k) || sh.failed) break;
 			Slot& s = slots[k];
 			const double t0 = now_s();
 			bool ok = true;
-			for (int i = 0; i < NI && ok; i++) {
-				if (parse_next(rd[i], chunk_reads, threads, s.pc[i]) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
-			}
-			if (!ok) break;
+			for (int i = 0; i < NI && ok; i++)
+				if (split_lines(rd[i], chunk_reads, s.pc[i]) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
 			for (int i = 0; i + 1 < NI && ok; i++)
 				for (int j = i + 1; j < NI && ok; j++)
 					if (s.pc[i].n != s.pc[j].n) {  // barcode_hmm.c:258-268
@@ -525,10 +667,31 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 						snprintf(b, sizeof b, "Input File:%s and %s differ in number of entries.", job->inputs[i].path, job->inputs[j].path);
 						sh.fail(TDG_EFORMAT, b); ok = false;
 					}
+			sec_split += now_s() - t0;
+			tr("split", k, t0);
 			if (!ok) break;
 			s.n = s.pc[0].n;
 			s.last = (s.n == 0);
+			q_conv.push(k);
+			if (s.last) break;
+		}
+		q_conv.close();
+	});
+
+	// ---- stage 1b: conversion + packing on the worker pool
+	std::thread t_parse([&] {
+		for (auto& t : t_alloc) t.join();
+		std::vector<int> run_max(NI);
+		for (int i = 0; i < NI; i++) run_max[i] = job->inputs[i].max_seq_len;
+		for (;;) {
+			int k;
+			if (!q_conv.pop(k) || sh.failed) break;
+			Slot& s = slots[k];
+			const double t0 = now_s();
+			bool ok = true;
 			if (!s.last) {
+				for (int i = 0; i < NI && ok; i++)
+					if (convert_chunk(s.pc[i], threads) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
 				for (int i = 0; i < NI && ok; i++) {
 					ParsedChunk& pc = s.pc[i];
 					// barcode_hmm.c:293-309: every read at least as long as the running maximum rebuilds the model
@@ -556,6 +719,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 				}
 			}
 			sec_parse += now_s() - t0;
+			tr("convert", k, t0);
 			if (!ok) break;
 			q_gpu.push(k);
 			if (s.last) break;
@@ -573,6 +737,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 				if (job->inputs[i].model && !s.last)
 					if (tdg_wait(s.batch[i], &s.res[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); return false; }
 			sec_gpu += now_s() - t0;
+			tr("gpu-wait", k, t0);
 			q_write.push(k);
 			return true;
 		};
@@ -710,6 +875,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			}
 			stats->total_read += n;
 			sec_write += now_s() - t0;
+			tr("write", k, t0);
 			q_free.push(k);
 		}
 		for (auto& tl : tally) {
@@ -723,16 +889,26 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 		q_free.close();
 	});
 
+	t_split.join();
+	if (sh.failed) { q_conv.close(); q_free.close(); }
 	t_parse.join();
 	if (sh.failed) { q_gpu.close(); q_free.close(); }
 	t_gpu.join();
 	if (sh.failed) { q_write.close(); q_free.close(); }
 	t_write.join();
-	for (auto& s : slots) for (auto* b : s.batch) if (b) tdg_batch_destroy(b);
+	double tq = now_s();
+	{
+		std::vector<std::thread> t_free;
+		for (auto& s : slots) for (auto* b : s.batch) if (b) t_free.emplace_back([b] { tdg_batch_destroy(b); });
+		for (auto& t : t_free) t.join();
+	}
+	tr("free-batches", -1, tq); tq = now_s();
 	close_readers();
+	tr("close-in", -1, tq); tq = now_s();
 	close_files();
+	tr("close-out", -1, tq);
 	stats->long_sequence_events = long_events.load();
-	stats->seconds_parse = sec_parse; stats->seconds_gpu_wait = sec_gpu; stats->seconds_write = sec_write;
+	stats->seconds_split = sec_split; stats->seconds_parse = sec_parse; stats->seconds_gpu_wait = sec_gpu; stats->seconds_write = sec_write;
 	stats->seconds_total = now_s() - t_start;
 	if (sh.failed) return tdg::set_last_error(sh.code, sh.msg.c_str());
 	return TDG_OK;

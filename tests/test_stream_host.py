@@ -209,3 +209,56 @@ def test_demux_unequal_files_error(tmp_path):
     with pytest.raises(TagdustError) as e:
         demux_run(None, [dict(path=tmp_path / "a.fq", model=None), dict(path=tmp_path / "b.fq", model=None)], tmp_path / "o", threads=2)
     assert "differ in number of entries" in str(e.value)
+
+
+def derived_stats(st, five_len, three_len):
+    """io.c:216-270 on the raw sums of tdg_sequence_stats (the same arithmetic integration/stats_fast.c does)."""
+    import math
+    out = {}
+    bg = [1.0 + st.base_count[k] for k in range(5)]
+    s = sum(bg)
+    out["background"] = [float(np.float32(math.log(float(np.float32(b / s))))) for b in bg]
+    def part(s0, s1, s2, L):
+        if not L:
+            return -1.0, -1.0
+        if s0 <= 1:
+            return float(L), 1.0
+        sd = math.sqrt((s0 * s2 - s1 ** 2.0) / (s0 * (s0 - 1.0)))
+        return s1 / s0, (sd if sd else 10000.0)
+    out["five"] = part(st.five_s0, st.five_s1, st.five_s2, five_len)
+    out["three"] = part(st.three_s0, st.three_s1, st.three_s2, three_len)
+    out["average_length"] = float(int(math.floor(st.sum_len / st.total_read + 0.5)))
+    out["max_seq_len"] = st.max_seq_len
+    return out
+
+
+@pytest.mark.parametrize("num_query", [1000, 1000001])
+def test_sequence_stats_match_reference(tmp_path, ref, num_query):
+    """tdg_sequence_stats (+ the derivation of io.c:216-270) vs the reference's get_sequence_stats, with 5' and 3'
+    partial segments whose matched length varies from read to read."""
+    from tagdust_b200.synth import encode
+    rng = np.random.default_rng(12)
+    five, three = "GGGTACGTAGG", "TTTCAGGCATT"
+    recs = []
+    for k in range(4200):
+        a = int(rng.integers(0, len(five) + 1)); b = int(rng.integers(0, len(three) + 1))
+        body = "".join(rng.choice(list("ACGTN"), size=int(rng.integers(20, 60)), p=[0.3, 0.2, 0.2, 0.29, 0.01]))
+        seq = five[a:] + body + three[:len(three) - b]
+        recs.append((f"r{k}", seq, "I" * len(seq)))
+    path = tmp_path / "p.fq"
+    write_fastq(path, recs)
+    p = ref.param_new(["P:" + five, "B:ACGT,TTGA", "R:N", "P:" + three])
+    out = np.zeros(13, np.float64)
+    ref.L.refh_sequence_stats.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+    assert ref.L.refh_sequence_stats(p, str(path).encode(), num_query, out.ctypes.data_as(C.c_void_p)) == 0
+    lib = _capi.load_library()
+    st = _capi.SeqStatsC()
+    f5, t3 = encode(five), encode(three)
+    rc = lib.tdg_sequence_stats(str(path).encode(), 0, num_query, f5.ctypes.data_as(_capi.c_uint8_p), len(five),
+                                t3.ctypes.data_as(_capi.c_uint8_p), len(three), 3, C.byref(st))
+    assert rc == 0 and st.total_read == 4200
+    d = derived_stats(st, len(five), len(three))
+    assert d["background"] == list(out[:5])
+    assert d["five"] == (out[7], out[8]) and d["three"] == (out[9], out[10])
+    assert d["average_length"] == out[11] and d["max_seq_len"] == int(out[12])
+    ref.param_free(p)
