@@ -90,6 +90,61 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (one wave of 75 776 reads) of the dominant
+    kernel, from the committed `ncu --set full` capture (profiles/ncu_traffic.json names the .ncu-rep)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as fh:
+        d = json.load(fh)
+    k = d.get("kernels", {}).get(kernel)
+    return (k["dram_bytes_read"] + k["dram_bytes_write"] if k else None), d.get("source")
+
+
+def write_fastq_fixed(path, codes, read_len):
+    """Fixed-width FASTQ records (name, 150 nt, '+', qualities) written with numpy, no Python loop."""
+    n = codes.shape[0]
+    name_w = 11
+    rec = np.empty((n, 1 + name_w + 1 + read_len + 3 + read_len + 1), np.uint8)
+    rec[:, 0] = ord("@")
+    idx = np.arange(n)
+    rec[:, 1] = ord("r")
+    for k in range(name_w - 1):
+        rec[:, 1 + name_w - 1 - k] = ord("0") + (idx // 10 ** k) % 10
+    o = 1 + name_w
+    rec[:, o] = ord("\n"); o += 1
+    rec[:, o:o + read_len] = np.frombuffer(b"ACGTN", np.uint8)[codes[:, :read_len]]; o += read_len
+    rec[:, o:o + 3] = np.frombuffer(b"\n+\n", np.uint8); o += 3
+    rec[:, o:o + read_len] = ord("I"); o += read_len
+    rec[:, o] = ord("\n")
+    rec.tofile(path)
+
+
+def files_e2e(ctx, model, tags, codes, n_reads, threads):
+    """FASTQ file -> tdg_demux_run (reader, pack, GPU, extraction, demultiplexed FASTQ files), the
+    streaming layer of SURVEY 8(f) rank 1.  Returns reads/s and the stage times."""
+    import shutil
+    import tempfile
+    from tagdust_b200 import stream
+    tmp = tempfile.mkdtemp(prefix="tdg_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        fq = os.path.join(tmp, "in.fq")
+        write_fastq_fixed(fq, codes[:n_reads], READ_LEN)
+        t0 = time.perf_counter()
+        st = stream.demux_run(ctx, [dict(path=fq, model=model, num_read_segments=1, threshold=THRESHOLD, max_seq_len=READ_LEN)],
+                              os.path.join(tmp, "out"), barcode_input=0, barcode_names=list(tags), minlen=16, dust=100, threads=threads)
+        dt = time.perf_counter() - t0
+        out_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.startswith("out"))
+        return {"value": n_reads / dt, "unit": "reads/s", "reads": n_reads, "seconds": dt, "host_threads": threads,
+                "input_bytes": os.path.getsize(fq), "output_bytes": out_bytes,
+                "stage_busy_s": {k: st[k] for k in ("seconds_split", "seconds_parse", "seconds_gpu_wait", "seconds_write")},
+                "extracted": st["num_EXTRACT_SUCCESS"],
+                "what": "tdg_demux_run: FASTQ file in /dev/shm -> 49 demultiplexed FASTQ files, byte-identical format to print_all"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -293,6 +348,15 @@ def run_gpu_arm(args):
                   "read_type_counts": tallies.tolist()},
     }
     line["roofline_whole_path"]["frac"] = line["roofline_whole_path"]["achieved"] / fp32_peak
+    traffic, traffic_src = ncu_traffic(dom)
+    line["roofline"]["traffic"] = traffic
+    line["roofline"]["traffic_source"] = traffic_src
+    line["roofline"]["algorithmic_hbm_bytes_per_launch"] = 148 * 512 * READ_LEN * (C - 49) * 8  # Mb/Ib of every stored column-position, once
+    if rank == 0 and world == 1 and not args.no_files:
+        try:
+            line["e2e_files"] = files_e2e(ctx, model, tags, codes, min(n_reads, args.files_reads), host_threads())
+        except Exception as exc:  # the streaming layer is an extra line, never a reason to lose the bench
+            line["e2e_files"] = {"error": str(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         n_cpu = max(threads * 500, 4000)
@@ -334,6 +398,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=32 * 148 * 512, help="reads per step per GPU (default 32 waves)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the FASTQ-file -> demultiplexed-files measurement")
+    ap.add_argument("--files-reads", type=int, default=2_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

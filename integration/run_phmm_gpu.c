@@ -103,7 +103,9 @@ tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param)
 	key = fnv(key, &mb->average_raw_length, sizeof(int));
 	tdg_model* out = NULL;
 	for (k = 0; k < MODEL_CACHE; k++)
-		if (g_models[k].m && g_models[k].key == key && g_models[k].max_len >= max_len) out = g_models[k].m;
+		/* same tables AND same length: a model sized for the long calibration reads would make every
+		 * wave of the real run smaller (scratch per read grows with max_len) */
+		if (g_models[k].m && g_models[k].key == key && g_models[k].max_len == max_len) out = g_models[k].m;
 	if (!out) {
 		tdg_model_desc d;
 		d.num_segments = S; d.total_hmms = H; d.total_columns = C; d.average_raw_length = mb->average_raw_length;
