@@ -39,7 +39,43 @@ constexpr int TDG_MAX_HMMS_DEV = 255;
 // base is the byte address of tab[(int)x]; no F2I (XU pipe) on the hot path.
 // ------------------------------------------------------------------------------------------
 constexpr int kPrefetchDist = 5;
+#ifndef TDG_AHEAD
+#define TDG_AHEAD 1
+#endif
+constexpr int kAhead = TDG_AHEAD;  // register prefetch distance (positions) of the silent-state loads in k_backward
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Silent-state arrays (silent_backward / silent_forward, ~90 MB per wave at cfg2) are re-read and
+// re-written once per HMM of a segment while 25 GB of Mb/Ib stream past them: they are accessed with
+// an L2 evict_last policy so that they stay resident in the 126 MB L2 (the Mb/Ib stream uses
+// evict-first __stcs/__ldcs).
+#ifndef TDG_SILENT_EVICT_LAST
+#define TDG_SILENT_EVICT_LAST 1
+#endif
+__device__ __forceinline__ uint64_t make_keep_policy()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ float ld_keep(const float* p, uint64_t pol)
+{
+#if TDG_SILENT_EVICT_LAST
+	float v;
+	asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+	return v;
+#else
+	return *p;
+#endif
+}
+__device__ __forceinline__ void st_keep(float* p, float v, uint64_t pol)
+{
+#if TDG_SILENT_EVICT_LAST
+	asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+	*p = v;
+#endif
+}
 
 typedef uint32_t TabAddr;  // shared-memory byte address of the table minus (0x4B000000 << 2)
 
@@ -211,6 +247,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 	float* cs_arr = sb + ((size_t)j * W) * kBlock;
 	const float* ps_arr = sb + ((size_t)(j + 1) * W) * kBlock;
 	const TabAddr tab = sm.tab;
+	const uint64_t keep = make_keep_policy();
 
 	for (int f = 0; f < sg.nh; ++f) {
 		const int c0 = sg.colbase + f * nc;
@@ -235,14 +272,24 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 		float* csp = cs_arr + (size_t)lw * kBlock;          // -> cs[i]
 		const float* psp = ps_arr + (size_t)lw * kBlock;    // -> ps[i]
 		float2* bwp = bw + ((size_t)c0 * a.lmax + (size_t)(lw - 1) * ncs) * kBlock;  // -> (position i, column 0)
-		float cs_n = *csp;
-		float ps_n = last_seg ? NEG_INF : *psp;
+		// silent-state values are loaded kAhead positions ahead of their use (they come from L2/HBM
+		// under a saturating store stream: one iteration of lead is not enough)
+		float cs_q[kAhead], ps_q[kAhead];
+#pragma unroll
+		for (int k = 0; k < kAhead; ++k) {
+			cs_q[k] = (lw - k >= 1) ? ld_keep(csp - (size_t)k * kBlock, keep) : NEG_INF;
+			ps_q[k] = (!last_seg && lw - k >= 1) ? ld_keep(psp - (size_t)k * kBlock, keep) : NEG_INF;
+		}
 		for (int i = lw; i >= 1; --i) {
 			const int x0 = sd.get();  // seqa[i]
-			float cs = cs_n;
-			const float ps0 = ps_n;
-			cs_n = *(csp - kBlock);
-			if (!last_seg) ps_n = *(psp - kBlock);
+			float cs = cs_q[0];
+			const float ps0 = ps_q[0];
+#pragma unroll
+			for (int k = 0; k + 1 < kAhead; ++k) { cs_q[k] = cs_q[k + 1]; ps_q[k] = ps_q[k + 1]; }
+			if (i > kAhead) {
+				cs_q[kAhead - 1] = ld_keep(csp - (size_t)kAhead * kBlock, keep);
+				if (!last_seg) ps_q[kAhead - 1] = ld_keep(psp - (size_t)kAhead * kBlock, keep);
+			}
 			if (i > kPrefetchDist) {  // pull the silent-state lines of iteration i-kPrefetchDist towards L1
 				prefetch_l1(csp - (size_t)kPrefetchDist * kBlock);
 				if (!last_seg) prefetch_l1(psp - (size_t)kPrefetchDist * kBlock);
@@ -316,7 +363,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 					}
 				}
 				if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // once per HMM f (:3604)
-				*csp = cs;
+				st_keep(csp, cs, keep);
 #pragma unroll UN
 				for (int g = 0; g < N; ++g) {
 					if (g < nc) { eMc[g] = eM0[g]; if (!STD) eIc[g] = eI0[g]; }
@@ -422,6 +469,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 	const bool first_seg = (j == 0);
 	const int skip_live = sg.skip_live;
 	const size_t bstep = (size_t)ncs * kBlock;
+	const uint64_t keep = make_keep_policy();
 
 	for (int f = 0; f < sg.nh; ++f) {
 		const int h = sg.hmmbase + f;
@@ -448,11 +496,11 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 		float* csp = cs_arr + kBlock;         // -> cs[i]
 		const float* psp = ps_arr + kBlock;   // -> ps[i]
 		float* pp = post + (size_t)h * kBlock;  // -> posterior (position i, hmm h)
-		float cs_n = *csp;
-		float ps_n = first_seg ? NEG_INF : *psp;
+		float cs_n = ld_keep(csp, keep);
+		float ps_n = first_seg ? NEG_INF : ld_keep(psp, keep);
 		// STDU: silent_backward of the next segment at position i+1 (= Mb of the unstored last column)
 		const float* qb = sbk + ((size_t)(j + 1) * W + 2) * kBlock;
-		float q_n = (STD && !last_seg) ? *qb : NEG_INF;
+		float q_n = (STD && !last_seg) ? ld_keep(qb, keep) : NEG_INF;
 		for (int i = 1; i <= lw; ++i) {
 			const int x = su.get();  // seqa[i]
 			float cs = cs_n;
@@ -461,7 +509,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 			if (STD) {
 				q0 = last_seg ? (i == len ? 0.0f : NEG_INF) : q_n;
 				qb += kBlock;
-				if (!last_seg && i < lw) q_n = *qb;
+				if (!last_seg && i < lw) q_n = ld_keep(qb, keep);
 			}
 			float2 bc[NB];
 			if (NC > 0) {
@@ -469,8 +517,8 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 #pragma unroll
 				for (int g = 0; g < NB; ++g) { bc[g] = bn[g]; bn[g] = __ldcs(&bwq[(size_t)g * kBlock]); }
 			}
-			cs_n = *(csp + kBlock);
-			if (!first_seg) ps_n = *(psp + kBlock);
+			cs_n = ld_keep(csp + kBlock, keep);
+			if (!first_seg) ps_n = ld_keep(psp + kBlock, keep);
 			if (i <= len) {
 				float P;
 				float oldMp, oldIp, newMp, D;
@@ -546,7 +594,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 					}
 				}
 				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
-				*csp = cs;
+				st_keep(csp, cs, keep);
 				// k_label's structured DP only reads posteriors inside [pfirst, plast] (below -104 exp()
 				// is exactly 0), so nothing is stored before the first position of that window
 				if (!(P < -104.0f)) { plast = i; pfirst = min(pfirst, i); }
