@@ -586,7 +586,20 @@ extern "C" int tdg_batch_append_codes(tdg_batch* b, int n, const uint8_t* codes,
 	for (int i = 0; i < n; i++) {
 		if (len[i] < 0 || len[i] > b->max_len) return fail(TDG_EINVAL, "read %d: length %d exceeds batch max_len %d", i, len[i], b->max_len);
 		if ((size_t)len[i] + 1 > stride) return fail(TDG_EINVAL, "read %d: stride %zu too small for length %d + terminator", i, stride, len[i]);
-		pack_read(b, b->n + i, codes + (size_t)i * stride, len[i]);
+	}
+	// every read owns its own words of the tile layout: large appends are packed on a few host threads
+	const int first = b->n;
+	int T = n >= (1 << 17) ? 4 : 1;
+	if (const char* e = getenv("TDG_PACK_THREADS")) T = std::max(1, atoi(e));
+	T = std::min(T, std::max(1, n / 4096));
+	auto work = [&](int lo, int hi) { for (int i = lo; i < hi; i++) pack_read(b, first + i, codes + (size_t)i * stride, len[i]); };
+	if (T <= 1) work(0, n);
+	else {
+		std::vector<std::thread> th;
+		const int per = (n + T - 1) / T;
+		for (int t = 1; t < T; t++) th.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+		work(0, std::min(n, per));
+		for (auto& x : th) x.join();
 	}
 	b->n += n;
 	return TDG_OK;
@@ -707,6 +720,7 @@ static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full)
 	const double budget = 0.90 * (double)(free_b + d.scratch_bytes);
 	const double per_cta = (double)kBlock * (double)(full ? m->slot_bytes_full : m->slot_bytes_bwd);
 	long fit = (long)(budget / per_cta);
+	if (const char* e = getenv("TDG_WAVE_CTAS")) { const long cap = atol(e); if (cap > 0) fit = std::min(fit, cap); }  // tests: force small waves
 	if (fit < 1) fit = 1;
 	return (int)std::min<long>(d.ctas, fit);
 }

@@ -231,3 +231,36 @@ def test_two_device_context_matches_single(oracle, ref):
     rep = compare(gpu, ora, lens, MODE_GET_LABEL, "2gpu")
     assert all(v == 0 for v in rep.values()), rep
     ctx.close(); ref.model_free(mb); ref.param_free(p)
+
+
+def test_small_waves_and_long_reads(gpu_ctx, oracle, ref, monkeypatch):
+    """Wave size is an execution detail: forcing 3-CTA waves (the path taken when the scratch of a
+    long-read model does not fit in HBM, e.g. threshold-calibration reads) gives identical bits; reads of
+    several hundred nt use the same kernels."""
+    rng = np.random.default_rng(21)
+    p, mb, desc = build_ref_model(ref, "b4_r", avg_len=300, max_len=700)
+    n = 4000
+    lens = rng.integers(200, 651, size=n).astype(np.int32)
+    codes = np.zeros((n, 656), np.uint8)
+    tags = [synth_encode(t) for t in CASES["b4_r"]["barcodes"]]
+    for r in range(n):
+        codes[r, : lens[r]] = rng.integers(0, 4, size=lens[r])
+        if r % 10:
+            codes[r, :6] = tags[r % 4]
+    base = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.0, minlen=16, dust=100)
+    monkeypatch.setenv("TDG_WAVE_CTAS", "3")
+    small = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.0, minlen=16, dust=100)
+    monkeypatch.delenv("TDG_WAVE_CTAS")
+    for k in SCORE_KEYS + ("read_type", "barcode", "fingerprint"):
+        assert np.array_equal(bits(base[k]), bits(small[k])), k
+    assert np.array_equal(base["labels"], small["labels"])
+    idx = np.arange(0, n, 40)
+    ora = oracle.run(desc, MODE_GET_LABEL, codes[idx], lens[idx], threshold=1.0, minlen=16, dust=100, threads=8)
+    rep = compare({k: v[idx] for k, v in base.items()}, ora, lens[idx], MODE_GET_LABEL, "long")
+    assert all(v == 0 for v in rep.values()), rep
+    ref.model_free(mb); ref.param_free(p)
+
+
+def synth_encode(s):
+    from tagdust_b200.synth import encode
+    return encode(s)
