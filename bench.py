@@ -95,11 +95,11 @@ def ncu_traffic(kernel):
     kernel, from the committed `ncu --set full` capture (profiles/ncu_traffic.json names the .ncu-rep)."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
-        return None, None
+        return None, None, {}
     with open(p) as fh:
         d = json.load(fh)
     k = d.get("kernels", {}).get(kernel)
-    return (k["dram_bytes_read"] + k["dram_bytes_write"] if k else None), d.get("source")
+    return (k["dram_bytes_read"] + k["dram_bytes_write"] if k else None), d.get("source"), (k or {})
 
 
 def write_fastq_fixed(path, codes, read_len):
@@ -348,10 +348,21 @@ def run_gpu_arm(args):
                   "read_type_counts": tallies.tolist()},
     }
     line["roofline_whole_path"]["frac"] = line["roofline_whole_path"]["achieved"] / fp32_peak
-    traffic, traffic_src = ncu_traffic(dom)
+    traffic, traffic_src, ncu_k = ncu_traffic(dom)
     line["roofline"]["traffic"] = traffic
     line["roofline"]["traffic_source"] = traffic_src
-    line["roofline"]["algorithmic_hbm_bytes_per_launch"] = 148 * 512 * READ_LEN * (C - 49) * 8  # Mb/Ib of every stored column-position, once
+    for key in ("issue_active_pct", "lsu_wavefronts_pct"):   # ncu: what the kernel is actually bound by per SM
+        if key in ncu_k:
+            line["roofline"][key] = ncu_k[key]
+    # the same kernel against the HBM roofline: algorithmic bytes = Mb/Ib of every stored (column, position), moved once
+    # (246 of the 295 columns are stored), per launch of one wave, over the event-timed duration
+    alg_bytes = 148 * 512 * READ_LEN * (C - 49) * 8
+    full_wave_s = dom_s / (args.steps * n_reads / (148 * 512)) if n_reads else 0.0   # duration per full wave of 75 776 reads
+    hbm_achieved = alg_bytes / full_wave_s / 1e9 if full_wave_s > 0 else 0.0
+    line["roofline_hbm"] = {"bound": "hbm", "kernel": dom, "achieved": hbm_achieved, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                            "frac": hbm_achieved / pk.get("hbm_gbs") if pk.get("hbm_gbs") else None, "traffic": traffic,
+                            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk_src,
+                            "note": "k_backward writes and k_forward reads this stream once; ncu traffic adds the silent-state arrays"}
     if rank == 0 and world == 1 and not args.no_files:
         try:
             line["e2e_files"] = files_e2e(ctx, model, tags, codes, min(n_reads, args.files_reads), host_threads())
@@ -359,7 +370,7 @@ def run_gpu_arm(args):
             line["e2e_files"] = {"error": str(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        n_cpu = max(threads * 500, 4000)
+        n_cpu = max(threads * 2500, 20000)   # ~10 s of host work
         kind, n_cpu, times = cpu_reference_rate(n_cpu, threads, seed=1234)
         cpu_value = n_cpu / times[0]
         line["cpu_baseline"] = {"value": cpu_value, "unit": "reads/s", "cores": threads, "kind": kind,
