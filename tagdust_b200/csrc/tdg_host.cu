@@ -402,6 +402,7 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 	if (!ctx || !out) return fail(TDG_EINVAL, "tdg_model_create: NULL argument");
 	*out = nullptr;
 	if (max_len < 1) return fail(TDG_EINVAL, "max_len must be >= 1");
+	if (max_len > 65000) return fail(TDG_EINVAL, "max_len %d too large (posterior windows are kept in 16 bits; limit 65000)", max_len);
 	auto* m = new tdg_model();
 	m->ctx = ctx;
 	m->max_len = max_len;
@@ -648,7 +649,7 @@ extern "C" int tdg_model_max_len(const tdg_model* m) { return m ? m->max_len : 0
 extern "C" int tdg_model_num_hmms(const tdg_model* m) { return m ? m->hm.H : 0; }
 extern "C" int tdg_model_set_max_len(tdg_model* m, int max_len)
 {
-	if (!m || max_len < 1) return fail(TDG_EINVAL, "bad argument");
+	if (!m || max_len < 1 || max_len > 65000) return fail(TDG_EINVAL, "bad argument (max_len 1..65000)");
 	std::lock_guard<std::mutex> model_lock(g_model_mu);
 	if (max_len <= m->max_len) return TDG_OK;
 	const HostModel& hm = m->hm;

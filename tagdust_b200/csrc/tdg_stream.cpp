@@ -572,7 +572,9 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	for (int i = 0; i < NI; i++) any_model |= job->inputs[i].model != nullptr;
 	if (any_model && !ctx) return failf(TDG_EINVAL, "tdg_demux_run: a GPU context is required");
 	const int threads = std::max(1, job->threads);
-	const int chunk_reads = job->chunk_reads > 0 ? job->chunk_reads : 2 * 148 * 512;
+	// default chunk: two waves per device of the context (a chunk is sharded contiguously over the devices)
+	const int ndev = ctx ? std::max(1, tdg_device_count(ctx)) : 1;
+	const int chunk_reads = job->chunk_reads > 0 ? job->chunk_reads : 2 * 148 * 512 * ndev;
 	const int nalt = job->num_alternatives;
 	if (nalt < 2) return failf(TDG_EINVAL, "num_alternatives must be >= 2");
 	const double t_start = now_s();
