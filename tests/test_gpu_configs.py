@@ -138,3 +138,77 @@ def test_cfg5_architecture_detection(gpu_ctx, oracle):
     small.close(); batch.close()
     for mo in models:
         mo.close()
+
+
+def test_cfg2_full_size_properties(gpu_ctx):
+    """BASELINE config 2 at (a multiple of) its full size through size-independent properties: the run is
+    streamed in batches of 32 waves with double buffering like a real job.  Default 20 M reads; set
+    TDG_FULL_SIZE=1 for the 100 M reads the config names.  Properties: the tallies of independently
+    generated batches follow the generating distribution (uniform barcodes within 2 %, the expected share of the
+    5 % contaminants picked up by chance), forward == backward likelihood, a checksum of per-read results is independent of
+    how the reads were batched, and every batch reproduces itself bit for bit when re-run at the end."""
+    import os
+    import zlib
+    from tagdust_b200.api import MODE_GET_LABEL
+    tags = TAGS6_ED3[:48]
+    desc = compile_architecture(["B:" + ",".join(tags), "R:N"], BG, 150.0, 150)
+    total = 100_000_000 if os.environ.get("TDG_FULL_SIZE") else 20_000_000
+    per = 32 * WAVE
+    nb = (total + per - 1) // per
+    model = gpu_ctx.model(desc, 150)
+    batches = [gpu_ctx.batch(per, 150) for _ in range(2)]
+    kw = dict(threshold=1.5, minlen=16, dust=100)
+    counts = np.zeros(49, np.int64)
+    n_model = n_model_ok = n_random = n_random_assigned = 0
+    first_crc = None
+    first_in = None
+    pending = None
+
+    def consume(res, truth):
+        nonlocal n_model, n_model_ok, n_random, n_random_assigned
+        ok = res["read_type"] == 0
+        bc = res["barcode"] & 0xFFFF
+        m = truth >= 0
+        n_model += int(m.sum()); n_model_ok += int((ok & m & (bc == truth)).sum())
+        n_random += int((~m).sum()); n_random_assigned += int((ok & ~m & (res["barcode"] != -1) & (bc < 48)).sum())
+        counts[:] += np.bincount(bc[ok & (res["barcode"] != -1)], minlength=49)[:49]
+        assert np.all(np.abs(res["f_score"] - res["b_score"]) < 5e-2)
+        return zlib.crc32(res["mapq"].tobytes() + res["barcode"].tobytes() + res["read_type"].tobytes())
+
+    for k in range(nb):
+        n = min(per, total - k * per)
+        codes, lens, truth = synth.make_reads_fast(n, 150, tags, error_rate=0.01, random_frac=0.05, seed=1000 + k)
+        b = batches[k % 2]
+        b.clear(); b.append(codes, lens)
+        gpu_ctx.submit(model, b, MODE_GET_LABEL, **kw)
+        if pending is not None:
+            crc = consume(gpu_ctx.wait(pending[0]), pending[1])
+            if first_crc is None:
+                first_crc = crc
+        if k == 0:
+            first_in = (codes, lens, truth)
+        pending = (b, truth)
+    crc = consume(gpu_ctx.wait(pending[0]), pending[1])
+    if first_crc is None:
+        first_crc = crc
+    assert n_model + n_random == total
+    assert n_model_ok / n_model > 0.995
+    # a uniform-random 6-mer is within one substitution of one of the 48 tags with probability 48*19/4096 = 22 %
+    assert 0.10 < n_random_assigned / n_random < 0.35
+    exp = counts[:48].sum() / 48.0
+    assert np.all(np.abs(counts[:48] - exp) < 0.02 * exp), counts
+    # the first batch again, split differently (one third / two thirds): same per-read bits -> same checksum
+    codes, lens, truth = first_in
+    cut = (len(lens) // 3) // 32 * 32 + 7
+    parts = []
+    for lo, hi in ((0, cut), (cut, len(lens))):
+        b = batches[0]
+        b.clear(); b.append(codes[lo:hi], lens[lo:hi])
+        gpu_ctx.submit(model, b, MODE_GET_LABEL, **kw)
+        parts.append(gpu_ctx.wait(b))
+    again = zlib.crc32(np.concatenate([p["mapq"] for p in parts]).tobytes() + np.concatenate([p["barcode"] for p in parts]).tobytes()
+                       + np.concatenate([p["read_type"] for p in parts]).tobytes())
+    assert again == first_crc
+    for b in batches:
+        b.close()
+    model.close()
