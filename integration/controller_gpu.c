@@ -82,6 +82,7 @@ int hmm_controller_multiple(struct parameters* param)
 		return ref(param);
 	}
 
+	tdg_shim_warmup();
 	struct sequence_stats_info** ssi = calloc(nf, sizeof *ssi);
 	struct model_bag** bags = calloc(nf, sizeof *bags);
 	char* read_present = calloc(nf, 1);

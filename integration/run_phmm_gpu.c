@@ -13,6 +13,8 @@
  * binaries live in integration/_build/, git-ignored).
  */
 #include <stddef.h>
+#include <pthread.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -31,7 +33,7 @@ static tdg_context* g_ctx = NULL;
 static tdg_batch* g_batch = NULL;
 static int g_batch_reads = 0, g_batch_len = 0;
 
-#define MODEL_CACHE 8
+#define MODEL_CACHE 24
 static struct { unsigned long long key; int max_len; tdg_model* m; } g_models[MODEL_CACHE];
 static int g_model_next = 0;
 
@@ -42,14 +44,39 @@ static int fail_msg(struct parameters* param, const char* what)
 	return kslFAIL;
 }
 
+static pthread_mutex_t g_ctx_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static int init_ctx_locked(void)
+{
+	int rc = TDG_OK;
+	pthread_mutex_lock(&g_ctx_mu);
+	if (!g_ctx) {
+		int n = 0; /* all visible devices */
+		const char* e = getenv("TDG_NUM_DEVICES");
+		if (e) n = atoi(e);
+		rc = tdg_init(n, NULL, &g_ctx);
+	}
+	pthread_mutex_unlock(&g_ctx_mu);
+	return rc;
+}
+
 static int ensure_ctx(struct parameters* param)
 {
-	if (g_ctx) return kslOK;
-	int n = 0; /* all visible devices */
-	const char* e = getenv("TDG_NUM_DEVICES");
-	if (e) n = atoi(e);
-	if (tdg_init(n, NULL, &g_ctx) != TDG_OK) return fail_msg(param, "tdg_init");
+	if (init_ctx_locked() != TDG_OK) return fail_msg(param, "tdg_init");
 	return kslOK;
+}
+
+/* CUDA start-up takes ~1.7 s on a B200 box: the controller starts it on a thread of its own while the
+ * reference's host set-up (sequence statistics, simulated calibration reads) runs.  A failure here is
+ * silent; the first real use retries on the calling thread and reports it. */
+static void* warmup_fn(void* arg) { (void)arg; (void)init_ctx_locked(); return NULL; }
+void tdg_shim_warmup(void)
+{
+	static int started = 0;
+	pthread_t th;
+	if (started) return;
+	started = 1;
+	if (pthread_create(&th, NULL, warmup_fn, NULL) == 0) pthread_detach(th);
 }
 
 /* FNV-1a over the flattened tables: a model_bag is rebuilt (same pointer or not) whenever the
@@ -67,7 +94,14 @@ tdg_context* tdg_shim_context(struct parameters* param)
 }
 
 /* struct model_bag -> tdg_model (flatten in segment -> hmm -> column order) */
+static tdg_model* get_model_len(struct model_bag* mb, struct parameters* param, int want_len);
+
 tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param)
+{
+	return get_model_len(mb, param, mb->current_dyn_length);   /* >= max_seq_len + 10 (barcode_hmm.c:5778) */
+}
+
+static tdg_model* get_model_len(struct model_bag* mb, struct parameters* param, int want_len)
 {
 	if (ensure_ctx(param) != kslOK) return NULL;
 	int S = mb->num_models, H = mb->total_hmm_num, C = 0, j, f, g, k, c = 0;
@@ -95,7 +129,7 @@ tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param)
 	}
 	seg_type[S] = 0;
 	for (j = 0; j < H; j++) { label[j] = mb->label[j]; for (k = 0; k < H; k++) T[j * H + k] = mb->transition_matrix[j][k]; }
-	const int max_len = mb->current_dyn_length;   /* >= max_seq_len + 10 (barcode_hmm.c:5778) */
+	const int max_len = want_len;
 	unsigned long long key = 1469598103934665603ULL;
 	key = fnv(key, seg_type, S); key = fnv(key, nh, 4 * S); key = fnv(key, nc, 4 * S); key = fnv(key, skip, 4 * S);
 	key = fnv(key, bg, 20); key = fnv(key, tr, 4 * C * 9); key = fnv(key, me, 4 * C * 5); key = fnv(key, ie, 4 * C * 5);
@@ -134,6 +168,13 @@ static int ensure_batch(struct parameters* param, int numseq, int max_len)
 	return kslOK;
 }
 
+static int by_length(const void* a, const void* b)
+{
+	const struct read_info* x = *(const struct read_info* const*)a;
+	const struct read_info* y = *(const struct read_info* const*)b;
+	return (x->len > y->len) - (x->len < y->len);
+}
+
 static int load_batch(struct parameters* param, struct read_info** ri, int numseq, int max_len)
 {
 	int i, ml = max_len;
@@ -145,11 +186,37 @@ static int load_batch(struct parameters* param, struct read_info** ri, int numse
 	return kslOK;
 }
 
+static double wall_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, struct parameters* param,
+                         struct fasta* reference_fasta, int numseq, int mode);
+
 int run_pHMM(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, struct parameters* param,
              struct fasta* reference_fasta, int numseq, int mode)
 {
+	const double t0 = wall_s();
+	const int rc = run_pHMM_impl(ab, mb, ri, param, reference_fasta, numseq, mode);
+	if (getenv("TDG_VERBOSE"))
+		fprintf(stderr, "tagdust_b200: run_pHMM mode %d, %d reads: %.3f s (called %.3f s after process start)\n", mode, numseq,
+		        wall_s() - t0, t0 - (double)0);
+	return rc;
+}
+
+static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, struct parameters* param,
+                         struct fasta* reference_fasta, int numseq, int mode)
+{
 	int i, j;
-	if (ensure_ctx(param) != kslOK) return kslFAIL;
+	{
+		const double t0 = wall_s();
+		const int first = (g_ctx == NULL);
+		if (ensure_ctx(param) != kslOK) return kslFAIL;
+		if (first && getenv("TDG_VERBOSE")) fprintf(stderr, "tagdust_b200: CUDA context + library start-up: %.3f s\n", wall_s() - t0);
+	}
 
 	if (mode == MODE_ARCH_COMP) {
 		if (!ab) return kslFAIL;
@@ -175,7 +242,48 @@ int run_pHMM(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, s
 
 	tdg_model* m = tdg_shim_get_model(mb, param);
 	if (!m) return fail_msg(param, "tdg_model_create");
-	if (load_batch(param, ri, numseq, 1) != kslOK) return kslFAIL;
+	/* MODE_GET_PROB (threshold calibration, calibrateQ.c:136): the simulated reads have a geometric length
+	 * tail (150 .. ~2000 nt at cfg2) and a warp walks its 32 reads to the longest of them, so the reads go to
+	 * the GPU sorted by length; results are per read and come back through the same permutation.  Only
+	 * ri->mapq and ri->bar_prob are observable after this call (labels are overwritten or freed), so the
+	 * label DP is skipped. */
+	struct read_info** order = ri;
+	if (mode == MODE_GET_PROB && numseq > 1) {
+		order = malloc(sizeof(struct read_info*) * numseq);
+		memcpy(order, ri, sizeof(struct read_info*) * numseq);
+		qsort(order, numseq, sizeof(struct read_info*), by_length);
+	}
+	if (mode == MODE_GET_PROB) {
+		/* sorted chunks, each scored with a model sized for the chunk's longest read: the scratch per read
+		 * (and with it the wave size) follows the length class instead of the longest simulated read */
+		const int CH = 65536;
+		int c0, rc = kslOK;
+		if (numseq <= 0) return kslOK;
+		tdg_run_params rq;
+		rq.confidence_threshold = param->confidence_threshold; rq.minlen = param->minlen;
+		rq.matchstart = param->matchstart; rq.matchend = param->matchend; rq.dust = 0; rq.want_labels = 0;
+		if (ensure_batch(param, numseq < CH ? numseq : CH, order[numseq - 1]->len > 1 ? order[numseq - 1]->len : 1) != kslOK) rc = kslFAIL;
+		for (c0 = 0; c0 < numseq && rc == kslOK; c0 += CH) {
+			const int n = numseq - c0 < CH ? numseq - c0 : CH;
+			const double tc = wall_s();
+			int ml = (order[c0 + n - 1]->len + 10 + 63) / 64 * 64;
+			tdg_result rs;
+			tdg_model* mc;
+			if (param->matchstart != -1 || param->matchend != -1) ml = mb->current_dyn_length;
+			if (ml > mb->current_dyn_length) ml = mb->current_dyn_length;
+			mc = get_model_len(mb, param, ml);
+			if (!mc) { rc = fail_msg(param, "tdg_model_create"); break; }
+			if (tdg_batch_clear(g_batch) != TDG_OK ||
+			    tdg_batch_append_records(g_batch, n, (const void* const*)(order + c0), offsetof(struct read_info, seq),
+			                             offsetof(struct read_info, len)) != TDG_OK) { rc = fail_msg(param, "tdg_batch_append_records"); break; }
+			if (tdg_run(g_ctx, mc, TDG_MODE_GET_PROB, &rq, g_batch, &rs) != TDG_OK) { rc = fail_msg(param, "tdg_run"); break; }
+			for (i = 0; i < n; i++) { order[c0 + i]->mapq = rs.mapq[i]; order[c0 + i]->bar_prob = rs.bar_prob[i]; }
+			if (getenv("TDG_VERBOSE")) fprintf(stderr, "tagdust_b200:   calibration chunk %d reads, max length %d: %.3f s\n", n, order[c0 + n - 1]->len, wall_s() - tc);
+		}
+		if (order != ri) free(order);
+		return rc;
+	}
+	if (load_batch(param, order, numseq, 1) != kslOK) { if (order != ri) free(order); return kslFAIL; }
 
 	tdg_run_params rp;
 	rp.confidence_threshold = param->confidence_threshold;
@@ -185,11 +293,13 @@ int run_pHMM(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, s
 	/* with -ref the reference order is extract -> match_to_reference -> dust (barcode_hmm.c:2345-2354):
 	 * keep dust on the host then, after the artifact filter */
 	rp.dust = reference_fasta ? 0 : param->dust;
-	rp.want_labels = 1;
+	rp.want_labels = (mode == MODE_GET_LABEL);
 	tdg_result res;
 	if (tdg_run(g_ctx, m, mode == MODE_GET_LABEL ? TDG_MODE_GET_LABEL : TDG_MODE_GET_PROB, &rp, g_batch, &res) != TDG_OK)
+	{
+		if (order != ri) free(order);
 		return fail_msg(param, "tdg_run");
-
+	}
 	for (i = 0; i < numseq; i++) {
 		struct read_info* r = ri[i];
 		const uint8_t* lab = res.labels + (size_t)i * res.label_stride;
@@ -197,7 +307,6 @@ int run_pHMM(struct arch_bag* ab, struct model_bag* mb, struct read_info** ri, s
 		if (param->matchstart != -1 || param->matchend != -1) wlen = param->matchend - param->matchstart;
 		r->mapq = res.mapq[i];
 		for (j = 0; j <= wlen; j++) r->labels[j] = (char)lab[j];
-		if (mode == MODE_GET_PROB) { r->bar_prob = res.bar_prob[i]; continue; }
 		r->bar_prob = 100;                                   /* barcode_hmm.c:2343 */
 		r->read_type = res.read_type[i];
 		if (res.barcode[i] != -1 || res.extracted[i]) { if (res.barcode[i] != -1) r->barcode = res.barcode[i]; }

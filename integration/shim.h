@@ -6,6 +6,8 @@ struct parameters;
 struct model_bag;
 /* the process-wide GPU context (created on first use; NULL + param->errmsg on failure) */
 tdg_context* tdg_shim_context(struct parameters* param);
+/* start creating the GPU context on a background thread (hides the CUDA start-up behind host set-up) */
+void tdg_shim_warmup(void);
 /* struct model_bag -> tdg_model through a small content-keyed cache; seg types come from param->read_structure */
 tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param);
 #endif

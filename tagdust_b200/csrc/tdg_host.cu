@@ -487,12 +487,14 @@ extern "C" void tdg_batch_destroy(tdg_batch* b)
 		if (s.copy) cudaStreamSynchronize(s.copy);
 		cudaStreamSynchronize(b->ctx->devs[k].compute);
 		cudaFree(s.slab);
+		cudaFree(s.labels);
 		if (s.h2d_done) cudaEventDestroy(s.h2d_done);
 		if (s.k_done) cudaEventDestroy(s.k_done);
 		if (s.d2h_done) cudaEventDestroy(s.d2h_done);
 		if (s.copy) cudaStreamDestroy(s.copy);
 	}
 	cudaFreeHost(b->h_slab);
+	cudaFreeHost(b->h_labels);
 	delete b;
 }
 
@@ -513,14 +515,15 @@ extern "C" int tdg_batch_create(tdg_context* ctx, int max_reads, int max_len, td
 		Carver cv;
 		const size_t o_seq = cv.take(N * b->words * 4), o_len = cv.take(N * 4), o_mapq = cv.take(N * 4), o_bp = cv.take(N * 4),
 		             o_f = cv.take(N * 4), o_b = cv.take(N * 4), o_r = cv.take(N * 4), o_rt = cv.take(N * 4), o_bc = cv.take(N * 4),
-		             o_fp = cv.take(N * 4), o_ex = cv.take(N), o_lab = cv.take(N * b->label_stride);
+		             o_fp = cv.take(N * 4), o_ex = cv.take(N);
 		char* base = nullptr;
 		if ((rc = pinned(&base, cv.total))) { tdg_batch_destroy(b); return rc; }
 		b->h_slab = base;
 		b->h_seq = (uint32_t*)(base + o_seq); b->h_len = (int32_t*)(base + o_len); b->h_mapq = (float*)(base + o_mapq);
 		b->h_bar_prob = (float*)(base + o_bp); b->h_f = (float*)(base + o_f); b->h_b = (float*)(base + o_b); b->h_r = (float*)(base + o_r);
 		b->h_read_type = (int32_t*)(base + o_rt); b->h_barcode = (int32_t*)(base + o_bc); b->h_fingerprint = (int32_t*)(base + o_fp);
-		b->h_extracted = (uint8_t*)(base + o_ex); b->h_labels = (uint8_t*)(base + o_lab);
+		b->h_extracted = (uint8_t*)(base + o_ex);
+		// label buffers (the largest part: max_len + 1 bytes per read) are created by the first submit that asks for labels
 	}
 	memset(b->h_seq, 0, N * b->words * 4);
 	const int nd = (int)ctx->devs.size();
@@ -536,14 +539,14 @@ extern "C" int tdg_batch_create(tdg_context* ctx, int max_reads, int max_len, td
 			Carver cv;
 			const size_t o_seq = cv.take(P * b->words * 4), o_len = cv.take(P * 4), o_mapq = cv.take(P * 4), o_bp = cv.take(P * 4),
 			             o_f = cv.take(P * 4), o_b = cv.take(P * 4), o_r = cv.take(P * 4), o_rt = cv.take(P * 4), o_bc = cv.take(P * 4),
-			             o_fp = cv.take(P * 4), o_ex = cv.take(P), o_lab = cv.take(P * b->label_stride);
+			             o_fp = cv.take(P * 4), o_ex = cv.take(P);
 			char* base = nullptr;
 			if ((rc = devalloc(&base, cv.total))) { tdg_batch_destroy(b); return rc; }
 			s.slab = base;
 			s.seq = (uint32_t*)(base + o_seq); s.len = (int32_t*)(base + o_len); s.mapq = (float*)(base + o_mapq);
 			s.bar_prob = (float*)(base + o_bp); s.f = (float*)(base + o_f); s.b = (float*)(base + o_b); s.r = (float*)(base + o_r);
 			s.read_type = (int32_t*)(base + o_rt); s.barcode = (int32_t*)(base + o_bc); s.fingerprint = (int32_t*)(base + o_fp);
-			s.extracted = (uint8_t*)(base + o_ex); s.labels = (uint8_t*)(base + o_lab);
+			s.extracted = (uint8_t*)(base + o_ex);
 		}
 		if (cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -805,6 +808,18 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	return launches;
 }
 
+static int ensure_label_buffers(tdg_batch* b)
+{
+	if (b->h_labels) return TDG_OK;
+	int rc;
+	if ((rc = pinned(&b->h_labels, (size_t)b->max_reads * b->label_stride))) return rc;
+	for (size_t k = 0; k < b->shard.size(); k++) {
+		CK(cudaSetDevice(b->ctx->devs[k].dev));
+		if ((rc = devalloc(&b->shard[k].labels, (size_t)b->shard[k].cap * b->label_stride))) return rc;
+	}
+	return TDG_OK;
+}
+
 static int check_compat(tdg_model* m, tdg_batch* b, const tdg_run_params* p)
 {
 	if (!m || !b) return fail(TDG_EINVAL, "NULL model or batch");
@@ -844,7 +859,7 @@ static int download_shard(tdg_batch* b, int k, cudaStream_t st, int mode, bool w
 	CK(cudaMemcpyAsync(b->h_bar_prob + f, s.bar_prob, n * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->h_f + f, s.f, n * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->h_r + f, s.r, n * 4, cudaMemcpyDeviceToHost, st));
-	if (want_labels) CK(cudaMemcpyAsync(b->h_labels + f * b->label_stride, s.labels, n * b->label_stride, cudaMemcpyDeviceToHost, st));
+	if (want_labels && b->h_labels) CK(cudaMemcpyAsync(b->h_labels + f * b->label_stride, s.labels, n * b->label_stride, cudaMemcpyDeviceToHost, st));
 	if (mode == TDG_MODE_GET_LABEL) {
 		CK(cudaMemcpyAsync(b->h_read_type + f, s.read_type, n * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(b->h_barcode + f, s.barcode, n * 4, cudaMemcpyDeviceToHost, st));
@@ -875,6 +890,7 @@ extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_ru
 	if (b->pending) return fail(TDG_EINVAL, "batch already submitted; call tdg_wait first");
 	assign_shards(b);
 	const bool want_labels = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p->want_labels);
+	if (want_labels && (rc = ensure_label_buffers(b))) return rc;
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
 		DeviceCtx& d = ctx->devs[k];
 		Shard& s = b->shard[k];
@@ -970,6 +986,7 @@ extern "C" int tdg_decode_resident(tdg_context* ctx, tdg_model* m, int mode, con
 	std::lock_guard<std::mutex> model_lock(g_model_mu);
 	int rc = check_compat(m, b, p);
 	if (rc) return rc;
+	if (mode != TDG_MODE_ARCH_COMP && (rc = ensure_label_buffers(b))) return rc;
 	int total = 0;
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
 		DeviceCtx& d = ctx->devs[k];
