@@ -86,7 +86,10 @@ typedef struct tdg_demux_input {
 	                                  R segment (run_rna_dust path, barcode_hmm.c:312-318) */
 	int32_t     num_read_segments; /* read_present[i]: R segments in the architecture = output reads of this file */
 	float       confidence_threshold; /* param->confidence_thresholds[i] */
-	int32_t     max_seq_len;       /* sequence_stats_info_container[i]->max_seq_len (for the "Long sequence found" count) */
+	int32_t     max_seq_len;       /* sequence_stats_info_container[i]->max_seq_len as the chunk loop sees it (threshold calibration
+	                                  raises it to its longest simulated read): the "Long sequence found" count starts from it */
+	int32_t     expected_len;      /* longest read get_sequence_stats saw in the file: sizes the staging batches (longer reads
+	                                  later in the file still work, the batch of that slot is re-created); 0 = max_seq_len */
 } tdg_demux_input;
 
 typedef struct tdg_demux_job {

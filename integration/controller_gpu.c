@@ -86,6 +86,7 @@ int hmm_controller_multiple(struct parameters* param)
 	struct sequence_stats_info** ssi = calloc(nf, sizeof *ssi);
 	struct model_bag** bags = calloc(nf, sizeof *bags);
 	char* read_present = calloc(nf, 1);
+	int* file_max_len = calloc(nf, sizeof(int));   /* longest read get_sequence_stats saw, before calibration raises ssi->max_seq_len */
 	long long barcode_present = 0;
 	int num_out_reads = 0;
 	param->read_structures = calloc(nf, sizeof(struct read_structure*));
@@ -137,6 +138,7 @@ int hmm_controller_multiple(struct parameters* param)
 		for (i = 0; i < nf; i++) {
 			param->read_structure = param->read_structures[i];
 			ssi[i] = get_sequence_stats(param, ri, i);
+			file_max_len[i] = ssi[i] ? ssi[i]->max_seq_len : 0;
 		}
 		free_read_info(ri, param->num_query);
 	}
@@ -201,6 +203,7 @@ int hmm_controller_multiple(struct parameters* param)
 			in[i].num_read_segments = read_present[i];
 			in[i].confidence_threshold = param->confidence_thresholds[i];
 			in[i].max_seq_len = ssi[i]->max_seq_len;
+			in[i].expected_len = file_max_len[i];
 			if (!(rs->num_segments == 1 && rs->type[0] == 'R')) need_gpu = 1;   /* :312 */
 		}
 		if (need_gpu && !(ctx = tdg_shim_context(param))) { status = kslFAIL; free(in); goto DONE; }
@@ -208,7 +211,9 @@ int hmm_controller_multiple(struct parameters* param)
 			struct read_structure* rs = param->read_structures[i];
 			if (rs->num_segments == 1 && rs->type[0] == 'R') continue;
 			param->read_structure = rs;
-			in[i].model = tdg_shim_get_model(bags[i], param);
+			/* sized for the reads of the file, not for the longest simulated calibration read
+			 * (estimateQthreshold raises ssi->max_seq_len, calibrateQ.c:121-126) */
+			in[i].model = tdg_shim_get_model_len(bags[i], param, file_max_len[i] + 10);
 			if (!in[i].model) {
 				snprintf(param->errmsg, kslibERRBUFSIZE, "tdg_model_create: %s", tdg_last_error());
 				status = kslFAIL; free(in); goto DONE;
@@ -276,7 +281,7 @@ DONE:
 		if (ssi[i]) free(ssi[i]);
 	}
 	param->read_structure = 0;
-	free(bags); free(ssi); free(read_present);
+	free(bags); free(ssi); free(read_present); free(file_max_len);
 	if (status != kslOK) fprintf(stderr, "%s\n", param->errmsg);
 	return status;
 }

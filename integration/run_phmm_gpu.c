@@ -96,6 +96,11 @@ tdg_context* tdg_shim_context(struct parameters* param)
 /* struct model_bag -> tdg_model (flatten in segment -> hmm -> column order) */
 static tdg_model* get_model_len(struct model_bag* mb, struct parameters* param, int want_len);
 
+tdg_model* tdg_shim_get_model_len(struct model_bag* mb, struct parameters* param, int max_len)
+{
+	return get_model_len(mb, param, max_len);
+}
+
 tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param)
 {
 	return get_model_len(mb, param, mb->current_dyn_length);   /* >= max_seq_len + 10 (barcode_hmm.c:5778) */

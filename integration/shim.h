@@ -10,4 +10,6 @@ tdg_context* tdg_shim_context(struct parameters* param);
 void tdg_shim_warmup(void);
 /* struct model_bag -> tdg_model through a small content-keyed cache; seg types come from param->read_structure */
 tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param);
+/* same tables, scratch sized for reads up to max_len (the tables do not depend on the read length) */
+tdg_model* tdg_shim_get_model_len(struct model_bag* mb, struct parameters* param, int max_len);
 #endif

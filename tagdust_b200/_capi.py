@@ -152,6 +152,7 @@ class DemuxInputC(C.Structure):
         ("num_read_segments", C.c_int32),
         ("confidence_threshold", C.c_float),
         ("max_seq_len", C.c_int32),
+        ("expected_len", C.c_int32),
     ]
 
 

@@ -60,6 +60,7 @@ def demux_run(ctx, inputs, outfile, *, barcode_input=-1, barcode_names=None, min
         arr[k].num_read_segments = it.get("num_read_segments", 1)
         arr[k].confidence_threshold = it.get("threshold", 0.0)
         arr[k].max_seq_len = it.get("max_seq_len", 0)
+        arr[k].expected_len = it.get("expected_len", 0)
     job = _capi.DemuxJobC()
     job.n_inputs = len(inputs)
     job.inputs = arr
