@@ -145,3 +145,21 @@ def test_index_only_file_via_arch_file(tmp_path):
         fh.write("tagdust -1 R:N\n")
         fh.write(f"tagdust -1 {BARC}\n")
     run_pair(tmp, "-arch arch.txt r1.fq i1.fq r2.fq")
+
+
+def test_architecture_selection_from_arch_file(tmp_path):
+    """-arch with several candidate lines for one input: test_architectures.c scores every candidate with
+    backward() over the first chunk (MODE_ARCH_COMP, per-thread float sums) and continues with the best one;
+    the log carries the selected architecture and its confidence, the output files its barcodes."""
+    tmp = str(tmp_path)
+    make_fastq(os.path.join(tmp, "in.fq"), 2400, [("F", 4), ("B", TAGS), ("R", None)], seed=11)
+    with open(os.path.join(tmp, "arch.txt"), "w") as fh:
+        fh.write(f"tagdust -1 {BARC} -2 R:N\n")
+        fh.write(f"tagdust -1 F:NNNN -2 {BARC} -3 R:N\n")
+        fh.write(f"tagdust -1 F:NNNNNNNN -2 {BARC} -3 R:N\n")
+        fh.write(f"tagdust -1 O:N -2 B:{','.join(TAGS[:3])} -3 S:GG -4 R:N\n")
+        fh.write("tagdust -1 R:N\n")
+    files = run_pair(tmp, "-arch arch.txt in.fq")
+    assert len(files) == len(TAGS) + 1
+    log = open(os.path.join(tmp, "gpu", "out_logfile.txt")).read()
+    assert "F:NNNN" in log and "Confidence" in log
