@@ -940,10 +940,42 @@ extern "C" int tdg_arch_compare(tdg_context* ctx, tdg_model* const* models, int 
 	if (num_threads < 1) num_threads = 1;
 	const int n = b->n;
 	std::vector<float> all((size_t)num_arch * n);
-	for (int a = 0; a < num_arch; a++) {
-		int rc = tdg_run(ctx, models[a], TDG_MODE_ARCH_COMP, nullptr, b, nullptr);
-		if (rc) return rc;
-		memcpy(all.data() + (size_t)a * n, b->h_b, (size_t)n * 4);
+	{
+		// One upload of the reads, the backward kernels of all architectures queued back to back on the
+		// device's compute stream (they share the scratch arena), one download of the A x n scores.
+		std::lock_guard<std::mutex> model_lock(g_model_mu);
+		if (b->pending) return fail(TDG_EINVAL, "batch already submitted; call tdg_wait first");
+		int rc;
+		for (int a = 0; a < num_arch; a++)
+			if ((rc = check_compat(models[a], b, nullptr))) return rc;
+		assign_shards(b);
+		const size_t nd = ctx->devs.size();
+		std::vector<float*> d_scores(nd, nullptr);
+		auto cleanup = [&] { for (size_t k = 0; k < nd; k++) if (d_scores[k]) { cudaSetDevice(ctx->devs[k].dev); cudaFree(d_scores[k]); } };
+		for (size_t k = 0; k < nd; k++) {
+			DeviceCtx& d = ctx->devs[k];
+			Shard& s = b->shard[k];
+			if (s.n == 0) continue;
+			CK(cudaSetDevice(d.dev));
+			if ((rc = devalloc(&d_scores[k], (size_t)num_arch * s.n))) { cleanup(); return rc; }
+			if ((rc = upload_shard(b, (int)k, s.copy))) { cleanup(); return rc; }
+			CK(cudaEventRecord(s.h2d_done, s.copy));
+			CK(cudaStreamWaitEvent(d.compute, s.h2d_done, 0));
+			for (int a = 0; a < num_arch; a++) {
+				const int wc = plan_wave_ctas(models[a], d, false);
+				if ((rc = ensure_scratch(d, scratch_need(models[a], false, wc)))) { cleanup(); return rc; }
+				if (queue_decode(ctx, models[a], TDG_MODE_ARCH_COMP, nullptr, b, (int)k, d.compute, d_scores[k] + (size_t)a * s.n, wc) < 0) { cleanup(); return TDG_ECUDA; }
+			}
+		}
+		for (size_t k = 0; k < nd; k++) {
+			Shard& s = b->shard[k];
+			if (s.n == 0) continue;
+			CK(cudaSetDevice(ctx->devs[k].dev));
+			CK(cudaStreamSynchronize(ctx->devs[k].compute));
+			for (int a = 0; a < num_arch; a++)
+				CK(cudaMemcpy(all.data() + (size_t)a * n + s.first, d_scores[k] + (size_t)a * s.n, (size_t)s.n * 4, cudaMemcpyDeviceToHost));
+		}
+		cleanup();
 	}
 	if (b_scores) memcpy(b_scores, all.data(), all.size() * 4);
 	// per-"thread" float sums in read order over the reference's static slices, added in thread order
