@@ -15,6 +15,7 @@ constexpr int kDpBlock = 128;
 constexpr int kColRec = 12;    // floats per column record (3 x float4)
 constexpr int kEmitRec = 10;   // eM[5], eI[5]
 constexpr int kMaxSources = 4; // label-DP predecessor sources per HMM (structured form)
+constexpr int kMaxStdCols = 16; // STDU segments with up to this many columns run fully unrolled kernels
 
 // Column record layout (floats), see barcode_hmm.h:87-96 for the transition indices:
 //  0 MM  1 MI  2 MD  3 II | 4 IM  5 DD  6 DM  7 MSKIP | 8 ISKIP  9 sM  10 sI  11 live-mask (int bits)

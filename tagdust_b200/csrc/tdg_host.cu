@@ -285,7 +285,7 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 	for (int s = 0; s < S; s++) {
 		SegInfo& g = hm.seg[s];
 		g.ta = g.tb = g.tb2 = g.tc = g.td = 0.0f;
-		if (g.nc < 3 || g.nc > 8) continue;
+		if (g.nc < 3) continue;  // up to kMaxStdCols columns the kernels are fully unrolled, beyond that they loop over the columns
 		const float* r0 = rec + (size_t)g.colbase * kColRec;
 		const float* e0 = emit + (size_t)g.colbase * kEmitRec;
 		const float ta = r0[F_MM], tb = r0[F_MI], tc = r0[F_II], td = r0[F_IM];

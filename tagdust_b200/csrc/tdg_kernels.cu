@@ -424,7 +424,15 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 				case 6: BWD_CASE(6, 1); break;
 				case 7: BWD_CASE(7, 1); break;
 				case 8: BWD_CASE(8, 1); break;
-				default: BWD_CASE(0, 0); break;
+				case 9: BWD_CASE(9, 1); break;
+				case 10: BWD_CASE(10, 1); break;
+				case 11: BWD_CASE(11, 1); break;
+				case 12: BWD_CASE(12, 1); break;
+				case 13: BWD_CASE(13, 1); break;
+				case 14: BWD_CASE(14, 1); break;
+				case 15: BWD_CASE(15, 1); break;
+				case 16: BWD_CASE(16, 1); break;
+				default: BWD_CASE(0, 1); break;  // standard pattern, more than kMaxStdCols columns: column loop
 			}
 		} else {
 			switch (nc) {
@@ -527,7 +535,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				{
 					const float* r = rec;
 					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
-					const float2 b = NC > 0 ? bc[0] : __ldcs(&bwq[((size_t)(i - 1) * nc) * kBlock]);
+					const float2 b = NC > 0 ? bc[0] : __ldcs(&bwq[((size_t)(i - 1) * ncs) * kBlock]);
 					const float eM = em[x], eI = STD ? eIu : em[5 + x];
 					const bool lsm = live_of<STD>(nc, 0, F_SM, lv);
 					const bool lsi = live_of<STD>(nc, 0, F_SI, lv);
@@ -559,8 +567,8 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 						const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
 						const uint32_t lp = STD ? 0u : __float_as_uint(rp[F_LIVE]);
 						float2 b;
-						if (STD && g == NC - 1) b = make_float2(q0 + trv<KIND>(r, sg, nc, g, F_MSKIP), NEG_INF);  // as k_backward computes it
-						else b = NC > 0 ? bc[(NC > 0 && !(STD && g == NC - 1)) ? g : 0] : __ldcs(&bwq[((size_t)(i - 1) * nc + g) * kBlock]);
+						if (STD && g == nc - 1) b = make_float2(q0 + trv<KIND>(r, sg, nc, g, F_MSKIP), NEG_INF);  // as k_backward computes it
+						else b = NC > 0 ? bc[(NC > 0 && !(STD && g == NC - 1)) ? g : 0] : __ldcs(&bwq[((size_t)(i - 1) * ncs + g) * kBlock]);
 						const float eM = em[g * kEmitRec + x], eI = STD ? eIu : em[g * kEmitRec + 5 + x];
 						const float oldMg = M[g], oldIg = I[g];
 						float v; bool have;
@@ -662,7 +670,15 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 				case 6: FWD_CASE(6, 1); break;
 				case 7: FWD_CASE(7, 1); break;
 				case 8: FWD_CASE(8, 1); break;
-				default: FWD_CASE(0, 0); break;
+				case 9: FWD_CASE(9, 1); break;
+				case 10: FWD_CASE(10, 1); break;
+				case 11: FWD_CASE(11, 1); break;
+				case 12: FWD_CASE(12, 1); break;
+				case 13: FWD_CASE(13, 1); break;
+				case 14: FWD_CASE(14, 1); break;
+				case 15: FWD_CASE(15, 1); break;
+				case 16: FWD_CASE(16, 1); break;
+				default: FWD_CASE(0, 1); break;
 			}
 		} else {
 			switch (nc) {

@@ -212,3 +212,33 @@ def test_cfg2_full_size_properties(gpu_ctx):
     for b in batches:
         b.close()
     model.close()
+
+
+@pytest.mark.parametrize("bl,umi", [(9, 0), (10, 10), (11, 0), (12, 12), (14, 13), (16, 15)])
+def test_long_barcodes_and_umis(gpu_ctx, oracle, ref, bl, umi):
+    """Barcodes / UMIs of 9-16 nt run the unrolled standard-pattern kernels (kMaxStdCols): parity with the
+    oracle and with the reference itself on ragged, N-containing reads."""
+    from refharness import background_logp
+    rng = np.random.default_rng(100 + bl)
+    tags = []
+    while len(tags) < 12:
+        t = "".join(rng.choice(list("ACGT"), size=bl))
+        if t not in tags:
+            tags.append(t)
+    segs = (["F:" + "N" * umi] if umi else []) + ["B:" + ",".join(tags), "R:N"]
+    n = 1200
+    codes, lens, truth = synth.make_reads(n, 70, tags, umi_len=umi, error_rate=0.02, random_frac=0.1, seed=bl, len_jitter=4, n_frac=0.01)
+    p = ref.param_new(segs, threshold=1.0, minlen=16, dust=100, threads=4)
+    mb = ref.model_new(p, background=background_logp((2501.0, 2480.0, 2510.0, 2492.0, 21.0)), average_length=70.0, max_seq_len=80)
+    desc = ref.flatten(mb, p)
+    kw = dict(threshold=1.0, minlen=16, dust=100)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, **kw)
+    ora = oracle.run(desc, MODE_GET_LABEL, codes, lens, threads=8, **kw)
+    rep = compare(gpu, ora, lens, MODE_GET_LABEL, "long-barcode")
+    assert all(v == 0 for v in rep.values()), rep
+    want = ref.run_phmm(mb, p, 1, codes[:300], lens[:300])          # the reference's own run_pHMM(MODE_GET_LABEL)
+    for k in ("mapq", "read_type", "barcode", "fingerprint"):
+        assert np.array_equal(bits(gpu[k][:300]), bits(np.asarray(want[k]).astype(gpu[k].dtype))), k
+    sel = (gpu["read_type"] == 0) & (truth >= 0)
+    assert ((gpu["barcode"][sel] & 0xFFFF) == truth[sel]).mean() > 0.99
+    ref.model_free(mb); ref.param_free(p)
