@@ -65,6 +65,7 @@ struct KArgs {
 	SegInfo seg[kMaxSegments];
 	const float* model_blob;   // device: [colrec C*12][emit C*10]
 	int32_t model_floats;      // floats to stage into shared memory after the logsum table
+	int32_t dyn_cols;          // columns of shared-memory profile state reserved for the column-loop paths (0 = none)
 	const float* logsum_tab;   // device: 16000 floats, entries >= 15700 zeroed
 	float r_step;              // log(1 - 1/avg) as float   (barcode_hmm.c:4520)
 	float r_end;               // log(1/avg) as float       (:4523)
@@ -108,6 +109,6 @@ int launch_backward(const KArgs& a, bool store, int ctas, void* stream);
 int launch_forward(const KArgs& a, int ctas, void* stream);
 int launch_label(const KArgs& a, int ctas_decode, void* stream);
 int kernels_configure(int smem_bytes); // sets the dynamic shared memory attributes once per device
-size_t decode_smem_bytes(int model_floats);
+size_t decode_smem_bytes(int model_floats, int dyn_cols);
 
 }  // namespace tdg

@@ -236,6 +236,7 @@ struct HostModel {  // derived, GPU independent
 	float bg[5];
 	float r_step = 0, r_end = 0;
 	int dead_terms = 0, std_segments = 0;
+	int loop_cols = 0;   // longest segment that runs a column-loop kernel path (0 = every segment is unrolled)
 };
 
 static bool is_ninf(float v) { return std::isinf(v) && v < 0; }
@@ -309,6 +310,11 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 			}
 		if (ok) { g.kind = 1; g.ta = ta; g.tb = tb; g.tb2 = tb2; g.tc = tc; g.td = td; hm.std_segments++; }
 	}
+	for (int s = 0; s < S; s++) {
+		const SegInfo& g = hm.seg[s];
+		const bool unrolled = (g.kind == 1) ? (g.nc >= 3 && g.nc <= kMaxStdCols) : (g.nc <= 8);
+		if (!unrolled) hm.loop_cols = std::max(hm.loop_cols, g.nc);
+	}
 	// labels, types
 	hm.label.assign(d->label, d->label + H);
 	hm.seg_type.assign((const uint8_t*)d->seg_type, (const uint8_t*)d->seg_type + S);
@@ -361,6 +367,7 @@ struct tdg_model {
 	int max_len = 0;
 	std::vector<ModelDev> dev;
 	size_t slot_bytes_full = 0, slot_bytes_bwd = 0;
+	int dyn_cols = 0;  // shared-memory profile state for the column-loop paths, when it fits beside the table and the model
 };
 
 extern "C" int tdg_model_validate(const tdg_model_desc* desc, char* errbuf, size_t errbuf_len)
@@ -410,7 +417,7 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 	int rc = derive_model(desc, m->hm, err);
 	if (rc != TDG_OK) { delete m; return fail(rc, "%s", err.c_str()); }
 	const HostModel& hm = m->hm;
-	const size_t smem = decode_smem_bytes((int)hm.blob.size());
+	size_t smem = decode_smem_bytes((int)hm.blob.size(), 0);
 	const size_t W = (size_t)max_len + 2;
 	m->slot_bytes_bwd = (size_t)hm.S * W * 4;
 	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
@@ -422,6 +429,8 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 			tdg_model_destroy(m);
 			return fail(TDG_EINVAL, "architecture too large for shared memory: needs %zu B, device allows %zu B", smem, d.smem_optin);
 		}
+		if (k == 0 && hm.loop_cols > 0 && decode_smem_bytes((int)hm.blob.size(), hm.loop_cols) + 64 <= d.smem_optin && !getenv("TDG_NO_SMEM_STATE"))
+			m->dyn_cols = hm.loop_cols;
 		cudaSetDevice(d.dev);
 		if ((int)smem > d.configured_smem) {
 			// allow the maximum once so later (larger) models need no reconfiguration
@@ -703,6 +712,7 @@ static void fill_model_args(KArgs& a, const tdg_model* m, int devk, const Device
 	for (int s = 0; s < hm.S; s++) a.seg[s] = hm.seg[s];
 	a.model_blob = m->dev[devk].blob;
 	a.model_floats = (int)hm.blob.size();
+	a.dyn_cols = m->dyn_cols;
 	a.logsum_tab = d.d_tab;
 	a.r_step = hm.r_step; a.r_end = hm.r_end;
 	for (int k = 0; k < 5; k++) a.bg[k] = hm.bg[k];

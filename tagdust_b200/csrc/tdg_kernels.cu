@@ -96,6 +96,23 @@ __device__ __forceinline__ float LS(float a, float b, TabAddr tab)
 	return mx + t;
 }
 
+// Per-read profile state M[g], I[g]: registers (fully unrolled paths), or -- for the column-loop paths of
+// long segments -- shared memory ([column][thread], conflict-free) when the host found room for it, else
+// thread-local arrays (which spill to L1/L2: the 227 KB shared-memory carve-out leaves ~28 KB of L1).
+template <int N>
+struct RegVec {
+	float v[N];
+	__device__ __forceinline__ float& operator[](int g) { return v[g]; }
+	__device__ __forceinline__ void bind(float*) {}
+};
+struct ShmVec {
+	float* p;
+	__device__ __forceinline__ float& operator[](int g) { return p[(size_t)g * kBlock]; }
+	__device__ __forceinline__ void bind(float* q) { p = q; }
+};
+template <int N, bool SMS> struct StateVec { typedef RegVec<N> type; };
+template <int N> struct StateVec<N, true> { typedef ShmVec type; };
+
 template <int NC, bool STD>
 struct Cols {
 	static constexpr int N = NC > 0 ? NC : kDynMaxCols;
@@ -112,6 +129,7 @@ struct Smem {
 	TabAddr tab;          // pre-offset shared address of the 16000 logsum entries
 	const float* colrec;  // C * 12
 	const float* emit;    // C * 10
+	float* dyn;           // [2 * dyn_cols][kBlock] profile state of the column-loop paths (this thread's lane), or unused
 };
 
 __device__ __forceinline__ Smem stage_smem(const KArgs& a, float* smem)
@@ -129,6 +147,7 @@ __device__ __forceinline__ Smem stage_smem(const KArgs& a, float* smem)
 	s.tab = s_tab_addr;
 	s.colrec = m;
 	s.emit = m + (size_t)a.C * kColRec;
+	s.dyn = m + a.model_floats + threadIdx.x;
 	return s;
 }
 
@@ -230,7 +249,7 @@ __device__ __forceinline__ float trv(const float* r, const SegInfo& sg, int nc, 
 // ahead (+ an L1 prefetch kPrefetchDist ahead): they come from L2/HBM and would otherwise
 // stall the ordered chain.  Scratch layout of one HMM: [position][column][512 lanes] float2.
 // ------------------------------------------------------------------------------------------
-template <int NC, int KIND, bool STORE>
+template <int NC, int KIND, bool STORE, bool SMS = false>
 __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, int x_term, bool last_seg,
                                             float2* __restrict__ bw, float* __restrict__ sb)
@@ -253,18 +272,25 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 		const int c0 = sg.colbase + f * nc;
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
 		const float* em = sm.emit + (size_t)c0 * kEmitRec;
-		float M[N], I[N], eMc[N];
-		float eIc[STD ? 1 : N];  // STDU: insert emissions are the same for every column of the segment
+		typename StateVec<N, SMS>::type M, I;
+		M.bind(sm.dyn); I.bind(sm.dyn + (size_t)a.dyn_cols * kBlock);
+		// emissions of the residue right of the current position (seqa[i+1]): kept in registers on the
+		// unrolled paths, looked up again from shared memory on the shared-state path (code xc)
+		float eMc[SMS ? 1 : N];
+		float eIc[(STD || SMS) ? 1 : N];  // STDU: insert emissions are the same for every column of the segment
+		int xc = x_term;
 		// state at i = len+1 : all -inf (:3466-3485); emissions of seqa[len+1] = a[len] (:3516)
 #pragma unroll UN
-		for (int g = 0; g < N; ++g) {
+		for (int g = 0; g < (NC > 0 ? N : nc); ++g) {
 			if (g < nc) {
 				M[g] = NEG_INF; I[g] = NEG_INF;
-				eMc[g] = em[g * kEmitRec + x_term];
-				if (!STD) eIc[g] = em[g * kEmitRec + 5 + x_term];
+				if (!SMS) {
+					eMc[SMS ? 0 : g] = em[g * kEmitRec + x_term];
+					if (!STD) eIc[(STD || SMS) ? 0 : g] = em[g * kEmitRec + 5 + x_term];
+				}
 			}
 		}
-		if (STD) eIc[0] = em[5 + x_term];
+		if (STD && !SMS) eIc[0] = em[5 + x_term];
 		const float sM0 = STD ? rec[F_SM] : 0.0f;
 		float ps1 = last_seg ? 0.0f : ps_arr[(size_t)(len + 1) * kBlock];
 		SeqDown sd;
@@ -295,18 +321,22 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 				if (!last_seg) prefetch_l1(psp - (size_t)kPrefetchDist * kBlock);
 			}
 			if (i <= len) {
-				float eM0[N];
-				float eI0[STD ? 1 : N];
+				float eM0[SMS ? 1 : N];
+				float eI0[(STD || SMS) ? 1 : N];
+				if (!SMS) {
 #pragma unroll UN
-				for (int g = 0; g < N; ++g) {
-					if (g < nc) {
-						eM0[g] = em[g * kEmitRec + x0];
-						if (!STD) eI0[g] = em[g * kEmitRec + 5 + x0];
+					for (int g = 0; g < (NC > 0 ? N : nc); ++g) {
+						if (g < nc) {
+							eM0[SMS ? 0 : g] = em[g * kEmitRec + x0];
+							if (!STD) eI0[(STD || SMS) ? 0 : g] = em[g * kEmitRec + 5 + x0];
+						}
 					}
+					if (STD) eI0[0] = em[5 + x0];
 				}
-				if (STD) eI0[0] = em[5 + x0];
-#define EIC(g) eIc[STD ? 0 : (g)]
-#define EI0(g) eI0[STD ? 0 : (g)]
+#define EMC(g) (SMS ? em[(g) * kEmitRec + xc] : eMc[SMS ? 0 : (g)])
+#define EM0(g) (SMS ? em[(g) * kEmitRec + x0] : eM0[SMS ? 0 : (g)])
+#define EIC(g) (SMS ? em[(STD ? 0 : (g)) * kEmitRec + 5 + xc] : eIc[(STD || SMS) ? 0 : (g)])
+#define EI0(g) (SMS ? em[(STD ? 0 : (g)) * kEmitRec + 5 + x0] : eI0[(STD || SMS) ? 0 : (g)])
 				// ---- last column (:3518-3541)
 				float oldMp, newMp, D;
 				{
@@ -314,9 +344,9 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
 					float nM = live_of<STD>(nc, m, F_MSKIP, lv) ? ps1 + trv<KIND>(r, sg, nc, m, F_MSKIP) : NEG_INF;
 					float nI = live_of<STD>(nc, m, F_ISKIP, lv) ? ps1 + r[F_ISKIP] : NEG_INF;
-					if (live_of<STD>(nc, m, F_IM, lv)) nI = LS(nI, M[m] + r[F_IM] + eMc[m], tab);
+					if (live_of<STD>(nc, m, F_IM, lv)) nI = LS(nI, M[m] + r[F_IM] + EMC(m), tab);
 					if (live_of<STD>(nc, m, F_II, lv)) nI = LS(nI, I[m] + r[F_II] + EIC(m), tab);
-					if (live_of<STD>(nc, m, F_SM, lv)) cs = LS(cs, nM + r[F_SM] + eM0[m], tab);
+					if (live_of<STD>(nc, m, F_SM, lv)) cs = LS(cs, nM + r[F_SM] + EM0(m), tab);
 					if (live_of<STD>(nc, m, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + EI0(m), tab);
 					oldMp = M[m]; newMp = nM; D = NEG_INF;
 					M[m] = nM; I[m] = nI;
@@ -324,7 +354,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 				}
 				// ---- columns m-1 .. 0 (:3545-3589)
 #pragma unroll UN
-				for (int gg = 1; gg < N; ++gg) {
+				for (int gg = 1; gg < (NC > 0 ? N : nc); ++gg) {
 					const int g = m - gg;
 					if (g >= 0) {
 						const int p = g + 1;
@@ -333,7 +363,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 						const float oldMg = M[g];
 						float v;
 						// M_backward[g][i]
-						v = live_of<STD>(nc, g, F_MM, lv) ? oldMp + eMc[p] + trv<KIND>(r, sg, nc, g, F_MM) : NEG_INF;
+						v = live_of<STD>(nc, g, F_MM, lv) ? oldMp + EMC(p) + trv<KIND>(r, sg, nc, g, F_MM) : NEG_INF;
 						if (live_of<STD>(nc, g, F_MSKIP, lv)) v = LS(v, ps1 + r[F_MSKIP], tab);
 						if (live_of<STD>(nc, g, F_MI, lv)) v = LS(v, I[g] + EIC(g) + trv<KIND>(r, sg, nc, g, F_MI), tab);
 						if (live_of<STD>(nc, g, F_MD, lv)) v = LS(v, D + trv<KIND>(r, sg, nc, g, F_MD), tab);
@@ -341,7 +371,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 						// I_backward[g][i]
 						v = live_of<STD>(nc, g, F_II, lv) ? I[g] + trv<KIND>(r, sg, nc, g, F_II) + EIC(g) : NEG_INF;
 						if (live_of<STD>(nc, g, F_ISKIP, lv)) v = LS(v, ps1 + r[F_ISKIP], tab);
-						if (live_of<STD>(nc, g, F_IM, lv)) v = LS(v, oldMp + trv<KIND>(r, sg, nc, g, F_IM) + eMc[p], tab);
+						if (live_of<STD>(nc, g, F_IM, lv)) v = LS(v, oldMp + trv<KIND>(r, sg, nc, g, F_IM) + EMC(p), tab);
 						const float nI = v;
 						// D_backward[g][i]
 						{
@@ -350,12 +380,12 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 							float dv = NEG_INF;
 							if (ldd) dv = D + trv<KIND>(r, sg, nc, g, F_DD);
 							if (ldm) {
-								const float t = newMp + eM0[p] + trv<KIND>(r, sg, nc, g, F_DM);
+								const float t = newMp + EM0(p) + trv<KIND>(r, sg, nc, g, F_DM);
 								dv = ldd ? LS(dv, t, tab) : t;
 							}
 							D = dv;
 						}
-						if (live_of<STD>(nc, g, F_SM, lv)) cs = LS(cs, nM + (STD ? sM0 : r[F_SM]) + eM0[g], tab);
+						if (live_of<STD>(nc, g, F_SM, lv)) cs = LS(cs, nM + (STD ? sM0 : r[F_SM]) + EM0(g), tab);
 						if (live_of<STD>(nc, g, F_SI, lv)) cs = LS(cs, nI + r[F_SI] + EI0(g), tab);
 						M[g] = nM; I[g] = nI;
 						oldMp = oldMg; newMp = nM;
@@ -365,11 +395,14 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 				if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // once per HMM f (:3604)
 				st_keep(csp, cs, keep);
 #pragma unroll UN
-				for (int g = 0; g < N; ++g) {
-					if (g < nc) { eMc[g] = eM0[g]; if (!STD) eIc[g] = eI0[g]; }
+				for (int g = 0; g < (NC > 0 ? N : nc); ++g) {
+					if (!SMS && g < nc) { eMc[SMS ? 0 : g] = eM0[SMS ? 0 : g]; if (!STD) eIc[(STD || SMS) ? 0 : g] = eI0[(STD || SMS) ? 0 : g]; }
 				}
-				if (STD) eIc[0] = eI0[0];
+				if (STD && !SMS) eIc[0] = eI0[0];
+				xc = x0;
 				ps1 = ps0;
+#undef EMC
+#undef EM0
 #undef EIC
 #undef EI0
 			}
@@ -416,6 +449,12 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 		const int kind = sg.kind;  // host-selected code path: 0 generic, 1 STD
 		const int nc = sg.nc;
 #define BWD_CASE(NCV, KINDV) bwd_segment<NCV, KINDV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb)
+// column-loop paths: profile state in shared memory when the host reserved room for this many columns
+#define BWD_LOOP(KINDV)                                                                                          \
+	do {                                                                                                         \
+		if (a.dyn_cols >= nc) bwd_segment<0, KINDV, STORE, true>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb); \
+		else BWD_CASE(0, KINDV);                                                                                 \
+	} while (0)
 		if (kind == 1) {
 			switch (nc) {
 				case 3: BWD_CASE(3, 1); break;
@@ -432,7 +471,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 				case 14: BWD_CASE(14, 1); break;
 				case 15: BWD_CASE(15, 1); break;
 				case 16: BWD_CASE(16, 1); break;
-				default: BWD_CASE(0, 1); break;  // standard pattern, more than kMaxStdCols columns: column loop
+				default: BWD_LOOP(1); break;  // standard pattern, more than kMaxStdCols columns: column loop
 			}
 		} else {
 			switch (nc) {
@@ -444,10 +483,11 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 				case 6: BWD_CASE(6, 0); break;
 				case 7: BWD_CASE(7, 0); break;
 				case 8: BWD_CASE(8, 0); break;
-				default: BWD_CASE(0, 0); break;
+				default: BWD_LOOP(0); break;
 			}
 		}
 #undef BWD_CASE
+#undef BWD_LOOP
 	}
 	if (valid) a.b_score[read] = sb[(size_t)1 * kBlock];  // model[0]->silent_backward[1] (:3610)
 }
@@ -456,7 +496,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
 // forward + posterior, one segment.  barcode_hmm.c:4199-4345
 // Mb/Ib of position i+1 (HBM), cs[i+1] and ps[i+1] are loaded one position ahead.
 // ------------------------------------------------------------------------------------------
-template <int NC, int KIND>
+template <int NC, int KIND, bool SMS = false>
 __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, float B,
                                             const float2* __restrict__ bw, const float* __restrict__ sbk,
@@ -485,10 +525,11 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
 		const float* em = sm.emit + (size_t)c0 * kEmitRec;
 		const float2* bwq = bw + (size_t)c0 * a.lmax * kBlock;  // -> (position 1, column 0); walks ahead of i
-		float M[N], I[N];
+		typename StateVec<N, SMS>::type M, I;
+		M.bind(sm.dyn); I.bind(sm.dyn + (size_t)a.dyn_cols * kBlock);
 		float2 bn[NB];
 #pragma unroll UN
-		for (int g = 0; g < N; ++g) {
+		for (int g = 0; g < (NC > 0 ? N : nc); ++g) {
 			if (g < nc) { M[g] = NEG_INF; I[g] = NEG_INF; }
 		}
 		if (NC > 0) {
@@ -496,6 +537,10 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 			for (int g = 0; g < NB; ++g) bn[g] = __ldcs(&bwq[(size_t)g * kBlock]);
 		}
 		const float sM0 = STD ? rec[F_SM] : 0.0f;
+		// column-loop path: Mb/Ib are fetched one stored column ahead of their use (column 0 of the next position
+		// while the last column of this one is computed), so the loads overlap the logsums instead of preceding them
+		float2 b_ahead = make_float2(NEG_INF, NEG_INF);
+		if (NC == 0) b_ahead = __ldcs(&bwq[0]);
 		float TP = NEG_INF;
 		int pfirst = 0xFFFF, plast = 0;  // positions whose posterior is >= -104 (exp != 0), for k_label
 		float ps1 = first_seg ? 0.0f : ps_arr[0];  // psilent[0]
@@ -535,7 +580,8 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				{
 					const float* r = rec;
 					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
-					const float2 b = NC > 0 ? bc[0] : __ldcs(&bwq[((size_t)(i - 1) * ncs) * kBlock]);
+					const float2 b = NC > 0 ? bc[0] : b_ahead;
+					if (NC == 0 && ncs > 1) b_ahead = __ldcs(&bwq[((size_t)(i - 1) * ncs + 1) * kBlock]);
 					const float eM = em[x], eI = STD ? eIu : em[5 + x];
 					const bool lsm = live_of<STD>(nc, 0, F_SM, lv);
 					const bool lsi = live_of<STD>(nc, 0, F_SI, lv);
@@ -559,7 +605,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				}
 				// ---- columns 1 .. nc-1 (:4270-4331)
 #pragma unroll UN
-				for (int g = 1; g < N; ++g) {
+				for (int g = 1; g < (NC > 0 ? N : nc); ++g) {
 					if (g < nc) {
 						const int p = g - 1;
 						const float* r = rec + g * kColRec;
@@ -568,7 +614,12 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 						const uint32_t lp = STD ? 0u : __float_as_uint(rp[F_LIVE]);
 						float2 b;
 						if (STD && g == nc - 1) b = make_float2(q0 + trv<KIND>(r, sg, nc, g, F_MSKIP), NEG_INF);  // as k_backward computes it
-						else b = NC > 0 ? bc[(NC > 0 && !(STD && g == NC - 1)) ? g : 0] : __ldcs(&bwq[((size_t)(i - 1) * ncs + g) * kBlock]);
+						else b = NC > 0 ? bc[(NC > 0 && !(STD && g == NC - 1)) ? g : 0] : b_ahead;
+						if (NC == 0) {
+							// next stored column of this position, or column 0 of the next position (clamped to the scratch)
+							if (g + 1 < ncs) b_ahead = __ldcs(&bwq[((size_t)(i - 1) * ncs + g + 1) * kBlock]);
+							else if (g + 1 == nc && i < a.lmax) b_ahead = __ldcs(&bwq[((size_t)i * ncs) * kBlock]);
+						}
 						const float eM = em[g * kEmitRec + x], eI = STD ? eIu : em[g * kEmitRec + 5 + x];
 						const float oldMg = M[g], oldIg = I[g];
 						float v; bool have;
@@ -662,6 +713,11 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 		const int kind = sg.kind;
 		const int nc = sg.nc;
 #define FWD_CASE(NCV, KINDV) fwd_segment<NCV, KINDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sbk, sf, post, tp, prange)
+#define FWD_LOOP(KINDV)                                                                              \
+	do {                                                                                             \
+		if (a.dyn_cols >= nc) fwd_segment<0, KINDV, true>(a, sm, sg, j, rd, off, len, lw, B, bw, sbk, sf, post, tp, prange);  \
+		else FWD_CASE(0, KINDV);                                                                     \
+	} while (0)
 		if (kind == 1) {
 			switch (nc) {
 				case 3: FWD_CASE(3, 1); break;
@@ -678,7 +734,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 				case 14: FWD_CASE(14, 1); break;
 				case 15: FWD_CASE(15, 1); break;
 				case 16: FWD_CASE(16, 1); break;
-				default: FWD_CASE(0, 1); break;
+				default: FWD_LOOP(1); break;
 			}
 		} else {
 			switch (nc) {
@@ -690,10 +746,11 @@ __global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
 				case 6: FWD_CASE(6, 0); break;
 				case 7: FWD_CASE(7, 0); break;
 				case 8: FWD_CASE(8, 0); break;
-				default: FWD_CASE(0, 0); break;
+				default: FWD_LOOP(0); break;
 			}
 		}
 #undef FWD_CASE
+#undef FWD_LOOP
 	}
 	if (!valid) return;
 	const TabAddr tab = sm.tab;
@@ -1053,7 +1110,10 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-size_t decode_smem_bytes(int model_floats) { return (size_t)(kLogsumSize + model_floats) * sizeof(float); }
+size_t decode_smem_bytes(int model_floats, int dyn_cols)
+{
+	return (size_t)(kLogsumSize + model_floats) * sizeof(float) + (size_t)2 * dyn_cols * kBlock * sizeof(float);
+}
 
 // smem_bytes = the device's opt-in maximum per block; each kernel's own static shared memory
 // is subtracted so that the dynamic limit requested is the largest the driver accepts.
@@ -1080,7 +1140,7 @@ int kernels_configure(int smem_bytes)
 
 int launch_backward(const KArgs& a, bool store, int ctas, void* stream)
 {
-	const size_t smem = decode_smem_bytes(a.model_floats);
+	const size_t smem = decode_smem_bytes(a.model_floats, a.dyn_cols);
 	if (store) k_backward<true><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
 	else k_backward<false><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
 	return (int)cudaGetLastError();
@@ -1088,7 +1148,7 @@ int launch_backward(const KArgs& a, bool store, int ctas, void* stream)
 
 int launch_forward(const KArgs& a, int ctas, void* stream)
 {
-	const size_t smem = decode_smem_bytes(a.model_floats);
+	const size_t smem = decode_smem_bytes(a.model_floats, a.dyn_cols);
 	k_forward<<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
 	return (int)cudaGetLastError();
 }

@@ -242,3 +242,45 @@ def test_long_barcodes_and_umis(gpu_ctx, oracle, ref, bl, umi):
     sel = (gpu["read_type"] == 0) & (truth >= 0)
     assert ((gpu["barcode"][sel] & 0xFFFF) == truth[sel]).mean() > 0.99
     ref.model_free(mb); ref.param_free(p)
+
+
+@pytest.mark.parametrize("smem_state", [True, False])
+@pytest.mark.parametrize("arch", ["long_partial", "long_linker"])
+def test_column_loop_paths(gpu_ctx, oracle, ref, arch, smem_state, monkeypatch):
+    """Segments longer than the unrolled kernels cover (P/O/G > 8 columns, standard pattern > 16) run the
+    column-loop paths, with the profile state in shared memory when it fits and in thread-local arrays
+    otherwise (TDG_NO_SMEM_STATE forces the latter): both against the oracle and the reference."""
+    from refharness import background_logp
+    if not smem_state:
+        monkeypatch.setenv("TDG_NO_SMEM_STATE", "1")
+    five, three = "AGGGAGGACGATGCGGTC", "GATCGGAAGAGCAC"
+    tags = TAGS6_ED3[:8]
+    if arch == "long_partial":
+        segs = ["P:" + five, "B:" + ",".join(tags), "R:N", "P:" + three]
+        kw_model = dict(five=(18.0, 15.2, 2.1), three=(14.0, 11.9, 1.7))
+        gen = dict(linker5=five, linker3=three)
+    else:
+        segs = ["S:ACGTACGGTTCAGCATGCAAGGCTAACG", "B:" + ",".join(tags), "R:N"]
+        kw_model = {}
+        gen = dict(linker5="ACGTACGGTTCAGCATGCAAGGCTAACG")
+    n = 1000
+    codes, lens, truth = synth.make_reads(n, 90, tags, error_rate=0.02, random_frac=0.1, seed=77, len_jitter=5, n_frac=0.01, **gen)
+    if arch == "long_partial":          # partial adapters: chop a random number of 5' bases off some reads
+        rng = np.random.default_rng(3)
+        for r in range(0, n, 3):
+            k = int(rng.integers(1, 12))
+            codes[r, : lens[r] - k] = codes[r, k: lens[r]].copy()
+            lens[r] -= k
+            codes[r, lens[r]:] = 0
+    p = ref.param_new(segs, threshold=1.0, minlen=16, dust=100, threads=4)
+    mb = ref.model_new(p, background=background_logp((2501.0, 2480.0, 2510.0, 2492.0, 21.0)), average_length=90.0, max_seq_len=100, **kw_model)
+    desc = ref.flatten(mb, p)
+    kw = dict(threshold=1.0, minlen=16, dust=100)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, **kw)
+    ora = oracle.run(desc, MODE_GET_LABEL, codes, lens, threads=8, **kw)
+    rep = compare(gpu, ora, lens, MODE_GET_LABEL, arch)
+    assert all(v == 0 for v in rep.values()), rep
+    want = ref.run_phmm(mb, p, 1, codes[:250], lens[:250])
+    for k in ("mapq", "read_type", "barcode", "fingerprint"):
+        assert np.array_equal(bits(gpu[k][:250]), bits(np.asarray(want[k]).astype(gpu[k].dtype))), k
+    ref.model_free(mb); ref.param_free(p)
