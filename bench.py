@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--reads", type=int, default=32 * 148 * 512, help="reads per step per GPU (default 32 waves)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the FASTQ-file -> demultiplexed-files measurement")
-    ap.add_argument("--files-reads", type=int, default=2_000_000)
+    ap.add_argument("--files-reads", type=int, default=4_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
