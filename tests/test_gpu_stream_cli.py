@@ -163,3 +163,37 @@ def test_architecture_selection_from_arch_file(tmp_path):
     assert len(files) == len(TAGS) + 1
     log = open(os.path.join(tmp, "gpu", "out_logfile.txt")).read()
     assert "F:NNNN" in log and "Confidence" in log
+
+
+def test_streaming_on_two_devices_matches_one(tmp_path):
+    """tdg_demux_run over a 2-GPU context (every chunk sharded contiguously over the devices) writes the
+    same bytes as over one GPU."""
+    import filecmp as fc
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cases import TAGS6_ED3
+    from refharness import background_logp
+    from tagdust_b200 import stream, synth
+    from tagdust_b200.api import Context, compile_architecture
+    import bench
+    tags = TAGS6_ED3[:24]
+    desc = compile_architecture(["B:" + ",".join(tags), "R:N"], background_logp((2.5e6, 2.5e6, 2.5e6, 2.5e6, 1.0)), 150.0, 150)
+    n = 400_000
+    codes, lens, _ = synth.make_reads_fast(n, 150, tags, seed=3)
+    fq = str(tmp_path / "in.fq")
+    bench.write_fastq_fixed(fq, codes, 150)
+    outs = []
+    for nd in (1, 2):
+        ctx = Context(nd)
+        model = ctx.model(desc, 150)
+        d = tmp_path / f"d{nd}"
+        d.mkdir()
+        st = stream.demux_run(ctx, [dict(path=fq, model=model, num_read_segments=1, threshold=1.5, max_seq_len=150)], str(d / "out"),
+                              barcode_input=0, barcode_names=list(tags), threads=8, chunk_reads=70_000)
+        assert st["total_read"] == n
+        outs.append(sorted(glob.glob(str(d / "out*.fq"))))
+        model.close(); ctx.close()
+    assert len(outs[0]) == 25 and [os.path.basename(x) for x in outs[0]] == [os.path.basename(x) for x in outs[1]]
+    for a, b in zip(*outs):
+        assert fc.cmp(a, b, shallow=False), os.path.basename(a)
