@@ -654,10 +654,9 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				}
 				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
 				st_keep(csp, cs, keep);
-				// k_label's structured DP only reads posteriors inside [pfirst, plast] (below -104 exp()
-				// is exactly 0), so nothing is stored before the first position of that window
+				// [pfirst, plast]: the window outside which exp(P) is exactly 0 (k_label skips HMMs without predecessors there)
 				if (!(P < -104.0f)) { plast = i; pfirst = min(pfirst, i); }
-				if (pfirst != 0xFFFF || !a.dp_structured) __stcs(pp, P);
+				__stcs(pp, P);
 				ps1 = ps0;
 			}
 			csp += kBlock; psp += kBlock; pp += (size_t)a.H * kBlock;
@@ -828,7 +827,7 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 {
 	__shared__ int s_src[TDG_MAX_HMMS_DEV * kMaxSources];
 	__shared__ uint8_t s_segflag[kMaxSegments];  // bit 0: no HMM of the segment has a predecessor but itself; bit 1: all share one source list
-	extern __shared__ float dsm[];  // structured path: D row [H][bs] floats, posterior ranges [H][bs] u32
+	extern __shared__ float dsm[];  // structured path: D row [H][bs] floats
 	const int bs = blockDim.x;
 	for (int k = threadIdx.x; k < a.H * kMaxSources; k += bs) s_src[k] = a.dp_src[k];
 	__syncthreads();
@@ -864,10 +863,10 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 		// row 0: exp(-inf) = 0 everywhere
 		for (int s = 0; s < a.S; ++s) { segmax[s] = 0.0f; segarg[s] = a.seg[s].hmmbase; }
 		if (a.dp_structured) {
-			// The DP row lives in shared memory and is updated in place from the highest HMM index
-			// down (every predecessor of j has a lower index, so it still holds row i-1).  Posterior
-			// entries outside [first,last] of their HMM (k_forward's prange) are < -104 and exp to
-			// exactly 0: they are neither stored by k_forward nor loaded here.
+			// The DP row lives in shared memory (4 H bytes per read: four 128-thread CTAs per SM) and is
+			// updated in place from the highest HMM index down (every predecessor of j has a lower index,
+			// so it still holds row i-1).  Posterior entries outside [first,last] of their HMM
+			// (k_forward's prange) are < -104 and exp to exactly 0.
 			//
 			// HMMs whose only predecessor is themselves (the first segment): D[i][j] = D[i-1][j] + p
 			// and path[i][j] = j, so outside their range nothing changes and no path byte is kept;
@@ -876,7 +875,6 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 			// incrementally: an entry that rises above the maximum, or ties it at a lower index, takes over.
 			constexpr int CH = 8;
 			float* D = dsm + threadIdx.x;
-			uint32_t* rng = (uint32_t*)(dsm + (size_t)H * bs) + threadIdx.x;
 			const uint32_t* prange = a.prange + (size_t)cta * H * kBlock + t;
 			int sfirst[kMaxSegments], slast[kMaxSegments];  // union of the posterior ranges of a segment's HMMs
 			for (int s = 0; s < a.S; ++s) {
@@ -886,7 +884,6 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 					const int j = hb + f;
 					const uint32_t r = prange[(size_t)j * kBlock];
 					D[(size_t)j * bs] = 0.0f;
-					rng[(size_t)j * bs] = r;
 					lo = min(lo, (int)(r & 0xFFFFu)); hi = max(hi, (int)(r >> 16));
 				}
 				sfirst[s] = lo; slast[s] = hi;
@@ -908,8 +905,7 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 								for (int k = 0; k < CH; ++k) {
 									const int f = f1 + k;
 									if (f < nh) {
-										const uint32_t r = rng[(size_t)(hb + f) * bs];
-										pv[k] = (i >= (int)(r & 0xFFFFu) && i <= (int)(r >> 16)) ? __ldcs(&row[(size_t)(hb + f) * kBlock]) : NEG_INF;
+										pv[k] = __ldcs(&row[(size_t)(hb + f) * kBlock]);  // < -104 outside the HMM's own window
 									}
 								}
 #pragma unroll
@@ -947,8 +943,7 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 							const int f = f1 - 1 - k;
 							if (f >= f0) {
 								const int j = hb + f;
-								const uint32_t r = rng[(size_t)j * bs];
-								pv[k] = (i >= (int)(r & 0xFFFFu) && i <= (int)(r >> 16)) ? __ldcs(&row[(size_t)j * kBlock]) : NEG_INF;
+								pv[k] = __ldcs(&row[(size_t)j * kBlock]);  // outside the HMM's window the posterior is < -104: post_exp() gives 0
 							}
 						}
 #pragma unroll
@@ -1159,8 +1154,8 @@ int launch_label(const KArgs& a, int ctas_decode, void* stream)
 	int bs = kDpBlock;
 	size_t smem = 0;
 	if (a.dp_structured) {
-		while (bs > 32 && (size_t)a.H * bs * 8 > 100 * 1024) bs >>= 1;  // keep >= 2 CTAs per SM
-		smem = (size_t)a.H * bs * 8;
+		while (bs > 32 && (size_t)a.H * bs * 4 > 54 * 1024) bs >>= 1;  // keep >= 4 CTAs per SM
+		smem = (size_t)a.H * bs * 4;
 	}
 	const int ctas = (threads + bs - 1) / bs;
 	k_label<<<ctas, bs, smem, (cudaStream_t)stream>>>(a);
