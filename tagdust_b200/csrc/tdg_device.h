@@ -97,6 +97,7 @@ struct KArgs {
 	const uint8_t* seg_type;   // [S]
 	const uint8_t* tmat;       // [H*H] 0/1 (generic label-DP fallback)
 	int32_t dp_structured;     // 1: dp_src describes T exactly
+	int32_t post_store_all;    // always 1 (see k_forward's posterior store)
 	// extraction
 	float confidence_threshold; int32_t minlen; int32_t required_finger_len; int32_t do_extract;
 	int32_t want_labels;

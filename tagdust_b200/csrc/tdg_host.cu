@@ -722,6 +722,7 @@ static void fill_model_args(KArgs& a, const tdg_model* m, int devk, const Device
 	a.seg_type = m->dev[devk].seg_type;
 	a.tmat = m->dev[devk].tmat;
 	a.dp_structured = hm.dp_structured;
+	a.post_store_all = 1;
 	a.required_finger_len = hm.required_finger_len;
 }
 
