@@ -75,6 +75,10 @@ int  tdg_sequence_stats(const char* path, int fasta, int num_query,
 int  tdg_batch_append_ragged(tdg_batch* b, int n, const uint8_t* codes, const uint64_t* seq_off,
                              const int32_t* len, int threads);
 
+/* Label buffers (max_len + 1 bytes per read, pinned + device) are created by the first submit that asks for
+ * labels; this creates them up front, e.g. on a set-up thread. */
+int  tdg_batch_reserve_labels(tdg_batch* b);
+
 /* `%0.2f` of a float exactly as fprintf prints ri->mapq (io.c:960-990); returns the length written. */
 int  tdg_format_rq(float mapq, char* out);
 

@@ -196,6 +196,7 @@ STREAM_PROTOTYPES = {
     "tdg_fastq_close": (None, [C.c_void_p]),
     "tdg_batch_append_ragged": (C.c_int, [C.c_void_p, C.c_int, c_uint8_p, C.POINTER(C.c_uint64), c_int32_p, C.c_int]),
     "tdg_format_rq": (C.c_int, [C.c_float, C.c_char_p]),
+    "tdg_batch_reserve_labels": (C.c_int, [C.c_void_p]),
     "tdg_demux_run": (C.c_int, [C.c_void_p, C.POINTER(DemuxJobC), C.POINTER(DemuxStatsC)]),
     "tdg_model_max_len": (C.c_int, [C.c_void_p]),
     "tdg_model_set_max_len": (C.c_int, [C.c_void_p, C.c_int]),

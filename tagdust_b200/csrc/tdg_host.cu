@@ -831,6 +831,12 @@ static int ensure_label_buffers(tdg_batch* b)
 	return TDG_OK;
 }
 
+extern "C" int tdg_batch_reserve_labels(tdg_batch* b)
+{
+	if (!b) return fail(TDG_EINVAL, "NULL batch");
+	return ensure_label_buffers(b);
+}
+
 static int check_compat(tdg_model* m, tdg_batch* b, const tdg_run_params* p)
 {
 	if (!m || !b) return fail(TDG_EINVAL, "NULL model or batch");

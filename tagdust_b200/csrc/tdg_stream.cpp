@@ -643,7 +643,8 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					Slot& s = slots[k];
 					s.batch_reads[i] = std::min(chunk_reads, 1 << 24);
 					s.batch_len[i] = job->inputs[i].expected_len > 0 ? job->inputs[i].expected_len : job->inputs[i].max_seq_len;
-					if (tdg_batch_create(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
+					if (tdg_batch_create(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK ||
+					    tdg_batch_reserve_labels(s.batch[i]) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
 				});
 	const bool trace = getenv("TDG_TRACE") != nullptr;
 	auto tr = [&](const char* stage, int k, double t0) {
@@ -868,12 +869,21 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					}
 				}
 			});
-			for (int f = 0; f < num_outfiles; f++) {
-				if (!files[f]) continue;
-				for (int t = 0; t < threads; t++) {
-					OutBuf& b = ob[t][f];
-					if (b.n && fwrite(b.d.data(), 1, b.n, files[f]) != b.n) { sh.fail(TDG_EIO, "write error on an output file"); break; }
-				}
+			// every file is written by one thread (its per-thread buffers in thread order = input order);
+			// different files go out in parallel: the copies into the page cache are the cost of this stage
+			{
+				std::atomic<int> next{0};
+				parallel_for(std::min(threads, 8), (size_t)std::min(threads, 8), 0, [&](size_t, size_t, int) {
+					for (;;) {
+						const int f = next.fetch_add(1);
+						if (f >= num_outfiles) break;
+						if (!files[f]) continue;
+						for (int t = 0; t < threads; t++) {
+							OutBuf& b = ob[t][f];
+							if (b.n && fwrite(b.d.data(), 1, b.n, files[f]) != b.n) { sh.fail(TDG_EIO, "write error on an output file"); break; }
+						}
+					}
+				});
 			}
 			stats->total_read += n;
 			sec_write += now_s() - t0;
