@@ -37,6 +37,14 @@ CASES = {
     # long linker (dynamic column path, > 8 columns)
     "s20_b_r": dict(segments=["S:ACGTACGGTTCAGCATGCAA", "B:" + ",".join(TAGS6_ED3[:8]), "R:N"], barcodes=TAGS6_ED3[:8],
                     read_len=70, gen=dict(error_rate=0.01, random_frac=0.05, linker5="ACGTACGGTTCAGCATGCAA")),
+    # 12-nt UMI + 12-nt barcodes (unrolled standard-pattern kernels for 9..16 columns)
+    "f12_b12_r": dict(segments=["F:NNNNNNNNNNNN", "B:ACGTTGCAACGT,TTGACCATGCAA,GGCATTACCGTA,CATGCATGGTAC,TACGGATCTAGC", "R:N"],
+                      barcodes=["ACGTTGCAACGT", "TTGACCATGCAA", "GGCATTACCGTA", "CATGCATGGTAC", "TACGGATCTAGC"], read_len=70,
+                      gen=dict(error_rate=0.02, random_frac=0.1, umi_len=12)),
+    # long partial adapters on both ends (column-loop kernel path, generic segments)
+    "p18_b_r_p14": dict(segments=["P:AGGGAGGACGATGCGGTC", "B:" + ",".join(TAGS6_ED4[:4]), "R:N", "P:GATCGGAAGAGCAC"], barcodes=TAGS6_ED4[:4],
+                        read_len=80, gen=dict(error_rate=0.02, random_frac=0.1, linker5="AGGGAGGACGATGCGGTC", linker3="GATCGGAAGAGCAC"),
+                        five=(18.0, 15.2, 2.1), three=(14.0, 11.9, 1.7)),
 }
 
 

@@ -25,7 +25,10 @@ THRESHOLD = 1.5
 
 def main():
     R = RefHarness()
+    only = set(sys.argv[1:])          # optional: regenerate just the named cases
     for name in CASES:
+        if only and name not in only:
+            continue
         codes, lens, truth = make_case_reads(name, N_READS, seed=23)
         p, mb, desc = build_ref_model(R, name, threshold=THRESHOLD)
         sc = R.decode_scores(mb, codes, lens)
