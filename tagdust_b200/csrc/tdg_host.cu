@@ -728,7 +728,7 @@ static void fill_model_args(KArgs& a, const tdg_model* m, int devk, const Device
 
 // CTAs (of kBlock reads) per wave: one per SM, fewer when the per-read scratch of a long-read model
 // (threshold calibration emits reads several times the average length) would not fit in HBM.
-static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full)
+static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full, int n_reads)
 {
 	size_t free_b = 0, total_b = 0;
 	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return d.ctas; }
@@ -737,7 +737,9 @@ static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full)
 	long fit = (long)(budget / per_cta);
 	if (const char* e = getenv("TDG_WAVE_CTAS")) { const long cap = atol(e); if (cap > 0) fit = std::min(fit, cap); }  // tests: force small waves
 	if (fit < 1) fit = 1;
-	return (int)std::min<long>(d.ctas, fit);
+	// a shard smaller than a wave needs scratch for its own CTAs only
+	const long need = std::max(1, (n_reads + kBlock - 1) / kBlock);
+	return (int)std::min<long>(std::min<long>(d.ctas, fit), need);
 }
 
 static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool full, int wave_ctas)
@@ -913,7 +915,7 @@ extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_ru
 		Shard& s = b->shard[k];
 		if (s.n == 0) continue;
 		CK(cudaSetDevice(d.dev));
-		const int wc = plan_wave_ctas(m, d, mode != TDG_MODE_ARCH_COMP);
+		const int wc = plan_wave_ctas(m, d, mode != TDG_MODE_ARCH_COMP, b->shard[k].n);
 		if ((rc = ensure_scratch(d, scratch_need(m, mode != TDG_MODE_ARCH_COMP, wc)))) return rc;
 		if ((rc = upload_shard(b, (int)k, s.copy))) return rc;
 		CK(cudaEventRecord(s.h2d_done, s.copy));
@@ -979,7 +981,7 @@ extern "C" int tdg_arch_compare(tdg_context* ctx, tdg_model* const* models, int 
 			CK(cudaEventRecord(s.h2d_done, s.copy));
 			CK(cudaStreamWaitEvent(d.compute, s.h2d_done, 0));
 			for (int a = 0; a < num_arch; a++) {
-				const int wc = plan_wave_ctas(models[a], d, false);
+				const int wc = plan_wave_ctas(models[a], d, false, s.n);
 				if ((rc = ensure_scratch(d, scratch_need(models[a], false, wc)))) { cleanup(); return rc; }
 				if (queue_decode(ctx, models[a], TDG_MODE_ARCH_COMP, nullptr, b, (int)k, d.compute, d_scores[k] + (size_t)a * s.n, wc) < 0) { cleanup(); return TDG_ECUDA; }
 			}
@@ -1041,7 +1043,7 @@ extern "C" int tdg_decode_resident(tdg_context* ctx, tdg_model* m, int mode, con
 		DeviceCtx& d = ctx->devs[k];
 		if (b->shard[k].n == 0) continue;
 		CK(cudaSetDevice(d.dev));
-		const int wc = plan_wave_ctas(m, d, mode != TDG_MODE_ARCH_COMP);
+		const int wc = plan_wave_ctas(m, d, mode != TDG_MODE_ARCH_COMP, b->shard[k].n);
 		if ((rc = ensure_scratch(d, scratch_need(m, mode != TDG_MODE_ARCH_COMP, wc)))) return rc;
 		// a caller-provided stream is only meaningful for a single-device context
 		cudaStream_t st = (ctx->devs.size() == 1) ? (cudaStream_t)cuda_stream : d.compute;

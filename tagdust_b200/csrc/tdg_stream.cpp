@@ -640,11 +640,13 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 		for (int i = 0; i < NI; i++)
 			if (job->inputs[i].model && (job->inputs[i].expected_len > 0 || job->inputs[i].max_seq_len > 0))
 				t_alloc.emplace_back([&, k, i] {
+					const double ta = now_s();
 					Slot& s = slots[k];
 					s.batch_reads[i] = std::min(chunk_reads, 1 << 24);
 					s.batch_len[i] = job->inputs[i].expected_len > 0 ? job->inputs[i].expected_len : job->inputs[i].max_seq_len;
 					if (tdg_batch_create(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK ||
 					    tdg_batch_reserve_labels(s.batch[i]) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
+					if (getenv("TDG_TRACE")) fprintf(stderr, "[trace] batch for slot %d input %d created in %.3f s\n", k, i, now_s() - ta);
 				});
 	const bool trace = getenv("TDG_TRACE") != nullptr;
 	auto tr = [&](const char* stage, int k, double t0) {
