@@ -366,8 +366,13 @@ static int convert_chunk(ParsedChunk& pc, int threads)
 extern "C" int tdg_fastq_next(tdg_fastq* f, int max_reads, int threads, tdg_fastq_chunk* chunk)
 {
 	if (!f || !chunk) return failf(TDG_EINVAL, "tdg_fastq_next: NULL argument");
-	int rc = split_lines(f, max_reads, f->own);
-	if (!rc) rc = convert_chunk(f->own, threads);
+	int rc;
+	try {
+		rc = split_lines(f, max_reads, f->own);
+		if (!rc) rc = convert_chunk(f->own, threads);
+	} catch (const std::bad_alloc&) {
+		rc = failf(TDG_EMEM, "out of host memory while reading %s", f->path.c_str());
+	}
 	memset(chunk, 0, sizeof *chunk);
 	if (rc) return rc;
 	const ParsedChunk& pc = f->own;
@@ -657,6 +662,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 
 	// ---- stage 1a: line splitting (sequential per file)
 	std::thread t_split([&] {
+		try {
 		for (;;) {
 			int k;
 			if (!q_free.pop(k) || sh.failed) break;
@@ -680,12 +686,14 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			q_conv.push(k);
 			if (s.last) break;
 		}
+		} catch (const std::bad_alloc&) { sh.fail(TDG_EMEM, "out of host memory in the line-splitting stage"); }
 		q_conv.close();
 	});
 
 	// ---- stage 1b: conversion + packing on the worker pool
 	std::thread t_parse([&] {
 		for (auto& t : t_alloc) t.join();
+		try {
 		std::vector<int> run_max(NI);
 		for (int i = 0; i < NI; i++) run_max[i] = job->inputs[i].max_seq_len;
 		for (;;) {
@@ -729,6 +737,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			q_gpu.push(k);
 			if (s.last) break;
 		}
+		} catch (const std::bad_alloc&) { sh.fail(TDG_EMEM, "out of host memory in the conversion stage"); }
 		q_gpu.close();
 	});
 
@@ -772,6 +781,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 
 	// ---- stage 3: post-process + write
 	std::thread t_write([&] {
+		try {
 		std::vector<std::vector<OutBuf>> ob((size_t)threads, std::vector<OutBuf>((size_t)num_outfiles));
 		std::vector<std::vector<int64_t>> tally((size_t)threads, std::vector<int64_t>(8, 0));
 		for (;;) {
@@ -900,6 +910,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			stats->num_EXTRACT_FAIL_MATCHES_ARTIFACTS += tl[5];
 			stats->num_EXTRACT_FAIL_LOW_COMPLEXITY += tl[6];
 		}
+		} catch (const std::bad_alloc&) { sh.fail(TDG_EMEM, "out of host memory in the writer stage"); }
 		q_free.close();
 	});
 
