@@ -101,6 +101,7 @@ struct KArgs {
 	// extraction
 	float confidence_threshold; int32_t minlen; int32_t required_finger_len; int32_t do_extract;
 	int32_t want_labels;
+	int32_t label_smem;        // set by launch_label: the read's labels are staged in shared memory
 };
 
 struct LaunchCfg { int ctas; };

@@ -830,9 +830,13 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 {
 	__shared__ int s_src[TDG_MAX_HMMS_DEV * kMaxSources];
 	__shared__ uint8_t s_segflag[kMaxSegments];  // bit 0: no HMM of the segment has a predecessor but itself; bit 1: all share one source list
+	__shared__ int s_hlabel[TDG_MAX_HMMS_DEV];    // mb->label
+	__shared__ uint8_t s_stype[kMaxSegments];     // read_structure->type
 	extern __shared__ float dsm[];  // structured path: D row [H][bs] floats
 	const int bs = blockDim.x;
 	for (int k = threadIdx.x; k < a.H * kMaxSources; k += bs) s_src[k] = a.dp_src[k];
+	for (int k = threadIdx.x; k < a.H; k += bs) s_hlabel[k] = a.hmm_label[k];
+	if ((int)threadIdx.x < a.S) s_stype[threadIdx.x] = a.seg_type[threadIdx.x];
 	__syncthreads();
 	if ((int)threadIdx.x < a.S) {
 		const int hb = a.seg[threadIdx.x].hmmbase, nh = a.seg[threadIdx.x].nh;
@@ -858,6 +862,21 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 	float* post = a.post + (size_t)cta * ((size_t)a.lmax * H) * kBlock + t;
 	uint8_t* path = a.path + (size_t)cta * ((size_t)a.lmax * H) * kBlock + t;
 	uint8_t* labels = a.labels + (size_t)read * a.label_stride;
+	// Labels of this read are staged in shared memory ([position][thread] bytes) when they fit: traceback and
+	// extraction then run without global round trips, and the row goes out as 32-bit words at the end.
+	uint8_t* slab = (uint8_t*)(dsm + (a.dp_structured ? (size_t)a.H * bs : 0)) + threadIdx.x;
+	const bool lsm = a.label_smem != 0;
+	auto lab_set = [&](int i, int v) { if (lsm) slab[(size_t)i * bs] = (uint8_t)v; else labels[i] = (uint8_t)v; };
+	auto lab_get = [&](int i) -> int { return lsm ? (int)slab[(size_t)i * bs] : (int)labels[i]; };
+	auto lab_flush = [&](int n) {  // n labels -> global row (label_stride is a multiple of 8, rows are 8-byte aligned)
+		if (!lsm) return;
+		for (int i = 0; i < n; i += 4) {
+			uint32_t w = 0;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) if (i + k < n) w |= (uint32_t)slab[(size_t)(i + k) * bs] << (8 * k);
+			*reinterpret_cast<uint32_t*>(labels + i) = w;
+		}
+	};
 
 	if (a.want_labels) {
 		float segmax[kMaxSegments];
@@ -986,13 +1005,14 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 				if (v > mx) { mx = v; move = j; }
 			}
 			// traceback (:4503-4514); an HMM without predecessors keeps the path on itself
-			for (int i = 0; i <= rlen; ++i) labels[i] = 0;
+			for (int i = 0; i <= rlen; ++i) lab_set(i, 0);
 			if (move < 0) move = 0;
-			labels[len] = (uint8_t)move;
+			lab_set(len, move);
 			for (int i = len; i > 0; --i) {
 				if (s_src[move * kMaxSources] != INT32_MIN) move = path[((size_t)(i - 1) * H + move) * kBlock];
-				labels[i - 1] = (uint8_t)move;
+				lab_set(i - 1, move);
 			}
+			lab_flush(rlen + 1);
 		} else {
 			// generic O(L*H^2) form, verbatim tie rules (:4453-4464)
 			for (int i = 1; i <= len; ++i) {
@@ -1017,13 +1037,14 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 				const float v = (len >= 1) ? post[((size_t)(len - 1) * H + j) * kBlock] : 0.0f;
 				if (v > mx) { mx = v; move = j; }
 			}
-			for (int i = 0; i <= rlen; ++i) labels[i] = 0;
+			for (int i = 0; i <= rlen; ++i) lab_set(i, 0);
 			if (move < 0) move = 0;
-			labels[len] = (uint8_t)move;
+			lab_set(len, move);
 			for (int i = len; i > 0; --i) {
 				move = path[((size_t)(i - 1) * H + move) * kBlock];
-				labels[i - 1] = (uint8_t)move;
+				lab_set(i - 1, move);
 			}
+			lab_flush(rlen + 1);
 		}
 	}
 	if (!a.do_extract) return;
@@ -1034,10 +1055,10 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 	const float mapq = a.mapq[read];
 	if (a.confidence_threshold <= mapq) {
 		for (int j = 0; j < len; ++j) {
-			const int c1 = a.hmm_label[labels[j + 1]];
+			const int c1 = s_hlabel[lab_get(j + 1)];
 			const int c2 = c1 & 0xFFFF;
 			const int c3 = (c1 >> 16) & 0x7FFF;
-			const uint8_t ty = a.seg_type[c2];
+			const uint8_t ty = s_stype[c2];
 			if (ty == 'F') { fingerlen++; key = (key << 2) | (rd.code(j + off) & 0x3); }
 			if (ty == 'B') {
 				hmm_has_barcode = 1; bar = c3;
@@ -1074,8 +1095,8 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 		auto e = [&](int j) -> int {
 			if (j >= rlen) return 0;  // NUL terminator
 			if (extracted) {
-				const int c2 = a.hmm_label[labels[j + 1]] & 0xFFFF;
-				if (a.seg_type[c2] != 'R') return 65;
+				const int c2 = s_hlabel[lab_get(j + 1)] & 0xFFFF;
+				if (s_stype[c2] != 'R') return 65;
 			}
 			return rd.code(j);
 		};
@@ -1160,8 +1181,13 @@ int launch_label(const KArgs& a, int ctas_decode, void* stream)
 		while (bs > 32 && (size_t)a.H * bs * 4 > 54 * 1024) bs >>= 1;  // keep >= 4 CTAs per SM
 		smem = (size_t)a.H * bs * 4;
 	}
+	// labels staged in shared memory when they fit beside the DP row without costing a resident CTA
+	KArgs b = a;
+	const size_t lab_bytes = (size_t)((a.lmax + 1 + 3) / 4 * 4) * bs;
+	b.label_smem = (b.want_labels && smem + lab_bytes <= 54 * 1024) ? 1 : 0;
+	if (b.label_smem) smem += lab_bytes;
 	const int ctas = (threads + bs - 1) / bs;
-	k_label<<<ctas, bs, smem, (cudaStream_t)stream>>>(a);
+	k_label<<<ctas, bs, smem, (cudaStream_t)stream>>>(b);
 	return (int)cudaGetLastError();
 }
 
