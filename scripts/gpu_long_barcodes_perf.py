@@ -44,3 +44,21 @@ ms = sum(v["ms"] for v in prof.values())
 cells = 2 * 150 * desc.total_columns
 print(f"S:24 + 48 barcodes: C={desc.total_columns}  {n / ms / 1e3:.2f} M reads/s  {n / ms * cells / 1e6:.0f} GCUPS  "
       + "  ".join(f"{k} {v['ms'] / v['launches']:.2f}" for k, v in prof.items()), flush=True)
+
+# partial 5' adapters (generic segments): 7 nt (unrolled, run-time masks) and 18 nt (column loop)
+for adapter in ("GGGGGGG", "AGGGAGGACGATGCGGTC"):
+    from tagdust_b200.api import compile_architecture as ca
+    L = len(adapter)
+    desc = ca(["P:" + adapter, "B:" + ",".join(tags), "R:N"], bench.background(), 150.0, 150, five=(float(L), L * 0.85, 1.5))
+    codes, lens, _ = synth.make_reads_fast(n, 150, [adapter + t for t in tags], seed=2)
+    model = ctx.model(desc, 150)
+    b = ctx.batch(n, 150); b.append(codes, lens); ctx.upload(b)
+    ctx.decode_resident(model, b, MODE_GET_LABEL, **kw); torch.cuda.synchronize()
+    ctx.profile_enable(True)
+    ctx.decode_resident(model, b, MODE_GET_LABEL, **kw); torch.cuda.synchronize()
+    prof = ctx.profile_read(0); ctx.profile_enable(False)
+    ms = sum(v["ms"] for v in prof.values())
+    cells = 2 * 150 * desc.total_columns
+    print(f"P:{L} + 48 barcodes: C={desc.total_columns}  {n / ms / 1e3:.2f} M reads/s  {n / ms * cells / 1e6:.0f} GCUPS  "
+          + "  ".join(f"{k} {v['ms'] / v['launches']:.2f}" for k, v in prof.items()), flush=True)
+    b.close(); model.close()

@@ -957,6 +957,50 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 						}
 					}
 					float cm = -1.0f; int ca = hb;
+					if (flag & 2) {
+						// One source list for the whole segment (the usual case: "everything in the previous
+						// segment"): the posteriors of the next chunk of HMMs are fetched while this chunk is
+						// folded, all loads of a chunk are issued before its first use, and where no posterior of
+						// the chunk survives exp() the update is max(self, best) without the double-precision exp.
+						float pn[CH];
+#pragma unroll
+						for (int k = 0; k < CH; ++k) {
+							const int f = nh - 1 - k;
+							pn[k] = (f >= 0) ? __ldcs(&row[(size_t)(hb + f) * kBlock]) : NEG_INF;
+						}
+						for (int f1 = nh; f1 > 0; f1 -= CH) {
+							float pv[CH], sv[CH];
+							bool any = false;
+#pragma unroll
+							for (int k = 0; k < CH; ++k) {
+								const int f = f1 - 1 - k;
+								pv[k] = pn[k];
+								sv[k] = (f >= 0) ? D[(size_t)(hb + f) * bs] : 0.0f;
+								any |= (f >= 0) && !(pv[k] < -104.0f);  // NaN posteriors (degenerate reads) take the exact path too
+							}
+#pragma unroll
+							for (int k = 0; k < CH; ++k) {  // next chunk (lower HMM indices)
+								const int f = f1 - CH - 1 - k;
+								pn[k] = (f >= 0) ? __ldcs(&row[(size_t)(hb + f) * kBlock]) : NEG_INF;
+							}
+#pragma unroll
+							for (int k = 0; k < CH; ++k) {
+								const int f = f1 - 1 - k;
+								if (f >= 0) {
+									const int j = hb + f;
+									const bool keep = sv[k] >= ubest;
+									const float mx = keep ? sv[k] : ubest;
+									float nd = mx;                           // exp() == 0: 0.0f + mx is mx
+									if (any) nd = post_exp(pv[k]) + mx;
+									if (!(keep && nd == sv[k])) D[(size_t)j * bs] = nd;
+									__stcs(&prow_path[(size_t)j * kBlock], (uint8_t)(keep ? j : uarg));
+									if (nd >= cm) { cm = nd; ca = j; }  // descending scan: >= leaves the first (lowest) maximum
+								}
+							}
+						}
+						nsegmax[s] = cm; nsegarg[s] = ca;
+						continue;
+					}
 					for (int f1 = nh; f1 > 0; f1 -= CH) {
 						const int f0 = f1 > CH ? f1 - CH : 0;
 						float pv[CH];
