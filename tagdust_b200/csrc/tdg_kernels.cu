@@ -959,43 +959,61 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 					float cm = -1.0f; int ca = hb;
 					if (flag & 2) {
 						// One source list for the whole segment (the usual case: "everything in the previous
-						// segment"): the posteriors of the next chunk of HMMs are fetched while this chunk is
-						// folded, all loads of a chunk are issued before its first use, and where no posterior of
-						// the chunk survives exp() the update is max(self, best) without the double-precision exp.
-						float pn[CH];
-#pragma unroll
-						for (int k = 0; k < CH; ++k) {
-							const int f = nh - 1 - k;
-							pn[k] = (f >= 0) ? __ldcs(&row[(size_t)(hb + f) * kBlock]) : NEG_INF;
+						// segment").  HMMs are folded from the highest index down in full chunks of CH with one
+						// base address per chunk (constant offsets, no per-element bounds tests); the posteriors of
+						// the next chunk are fetched while this one is folded; where no posterior of a chunk
+						// survives exp() the update is max(self, best) without the double-precision exp; outside
+						// the union of the segment's posterior windows nothing is loaded at all.
+						const bool inwin = (i >= sfirst[s] && i <= slast[s]);
+						auto fold = [&](int j, float p, float self) {
+							const bool keep = self >= ubest;
+							const float mx = keep ? self : ubest;
+							const float nd = post_exp(p) + mx;
+							D[(size_t)j * bs] = nd;
+							__stcs(&prow_path[(size_t)j * kBlock], (uint8_t)(keep ? j : uarg));
+							if (nd >= cm) { cm = nd; ca = j; }  // descending scan: >= leaves the first (lowest) maximum
+						};
+						int f1 = nh;
+						for (; f1 > (nh / CH) * CH; --f1) {  // the nh % CH highest HMMs one by one
+							const int j = hb + f1 - 1;
+							fold(j, inwin ? __ldcs(&row[(size_t)j * kBlock]) : NEG_INF, D[(size_t)j * bs]);
 						}
-						for (int f1 = nh; f1 > 0; f1 -= CH) {
+						float pn[CH];
+						if (f1 > 0) {
+							const float* rb = row + (size_t)(hb + f1 - CH) * kBlock;
+#pragma unroll
+							for (int k = 0; k < CH; ++k) pn[k] = inwin ? __ldcs(&rb[(size_t)(CH - 1 - k) * kBlock]) : NEG_INF;
+						}
+						for (; f1 > 0; f1 -= CH) {
+							const int jb = hb + f1 - CH;  // lowest HMM of the chunk; element k is HMM jb + CH-1-k
+							float* Db = D + (size_t)jb * bs;
+							uint8_t* pb = prow_path + (size_t)jb * kBlock;
 							float pv[CH], sv[CH];
 							bool any = false;
 #pragma unroll
 							for (int k = 0; k < CH; ++k) {
-								const int f = f1 - 1 - k;
 								pv[k] = pn[k];
-								sv[k] = (f >= 0) ? D[(size_t)(hb + f) * bs] : 0.0f;
-								any |= (f >= 0) && !(pv[k] < -104.0f);  // NaN posteriors (degenerate reads) take the exact path too
+								sv[k] = Db[(size_t)(CH - 1 - k) * bs];
+								any |= !(pv[k] < -104.0f);  // NaN posteriors (degenerate reads) take the exact path too
 							}
+							if (f1 > CH) {
+								const float* rb = row + (size_t)(jb - CH) * kBlock;
 #pragma unroll
-							for (int k = 0; k < CH; ++k) {  // next chunk (lower HMM indices)
-								const int f = f1 - CH - 1 - k;
-								pn[k] = (f >= 0) ? __ldcs(&row[(size_t)(hb + f) * kBlock]) : NEG_INF;
+								for (int k = 0; k < CH; ++k) pn[k] = inwin ? __ldcs(&rb[(size_t)(CH - 1 - k) * kBlock]) : NEG_INF;
 							}
+							if (!any) {
 #pragma unroll
-							for (int k = 0; k < CH; ++k) {
-								const int f = f1 - 1 - k;
-								if (f >= 0) {
-									const int j = hb + f;
+								for (int k = 0; k < CH; ++k) {
+									const int j = jb + CH - 1 - k;
 									const bool keep = sv[k] >= ubest;
-									const float mx = keep ? sv[k] : ubest;
-									float nd = mx;                           // exp() == 0: 0.0f + mx is mx
-									if (any) nd = post_exp(pv[k]) + mx;
-									if (!(keep && nd == sv[k])) D[(size_t)j * bs] = nd;
-									__stcs(&prow_path[(size_t)j * kBlock], (uint8_t)(keep ? j : uarg));
-									if (nd >= cm) { cm = nd; ca = j; }  // descending scan: >= leaves the first (lowest) maximum
+									const float nd = keep ? sv[k] : ubest;   // exp() == 0: 0.0f + mx is mx
+									if (!keep) Db[(size_t)(CH - 1 - k) * bs] = nd;
+									__stcs(&pb[(size_t)(CH - 1 - k) * kBlock], (uint8_t)(keep ? j : uarg));
+									if (nd >= cm) { cm = nd; ca = j; }
 								}
+							} else {
+#pragma unroll
+								for (int k = 0; k < CH; ++k) fold(jb + CH - 1 - k, pv[k], sv[k]);
 							}
 						}
 						nsegmax[s] = cm; nsegarg[s] = ca;
