@@ -262,3 +262,23 @@ def test_sequence_stats_match_reference(tmp_path, ref, num_query):
     assert d["five"] == (out[7], out[8]) and d["three"] == (out[9], out[10])
     assert d["average_length"] == out[11] and d["max_seq_len"] == int(out[12])
     ref.param_free(p)
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_demux_tiny_chunks_and_pipes(tmp_path, gz):
+    """Chunk boundaries in the middle of blocks, pipe input (zcat) with carried-over tails, three slots recycled
+    many times: the output is still the reference CLI's, byte for byte."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    tmp = str(tmp_path)
+    rng = np.random.default_rng(17)
+    recs = random_records(rng, 4321, lo=17, hi=140)
+    suffix = ".fq.gz" if gz else ".fq"
+    write_fastq(os.path.join(tmp, "in" + suffix), recs)
+    cpu = run_ref_cli(tmp, f"-Q 3 -1 R:N in{suffix}", "out")
+    mine = os.path.join(tmp, "mine"); os.makedirs(mine)
+    st = demux_run(None, [dict(path=os.path.join(tmp, "in" + suffix), model=None, num_read_segments=1)],
+                   os.path.join(mine, "out"), dust=100, threads=3, chunk_reads=97)
+    assert st["total_read"] == 4321
+    for name in ("out.fq", "out_un.fq"):
+        assert filecmp.cmp(os.path.join(cpu, name), os.path.join(mine, name), shallow=False), name
