@@ -49,6 +49,7 @@ static void say(struct parameters* param, const char* fmt, ...)
 
 static void die(struct parameters* param)
 {
+	tdg_shim_warmup_join();
 	free_param(param);
 	exit(EXIT_FAILURE);
 }
@@ -276,6 +277,7 @@ int hmm_controller_multiple(struct parameters* param)
 	}
 
 DONE:
+	tdg_shim_warmup_join();
 	for (i = 0; i < nf; i++) {
 		if (bags[i]) free_model_bag(bags[i]);
 		if (ssi[i]) free(ssi[i]);

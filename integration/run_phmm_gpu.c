@@ -70,13 +70,18 @@ static int ensure_ctx(struct parameters* param)
  * reference's host set-up (sequence statistics, simulated calibration reads) runs.  A failure here is
  * silent; the first real use retries on the calling thread and reports it. */
 static void* warmup_fn(void* arg) { (void)arg; (void)init_ctx_locked(); return NULL; }
+static pthread_t g_warm_thread;
+static int g_warm_state = 0;   /* 0 not started, 1 running / joinable, 2 joined */
 void tdg_shim_warmup(void)
 {
-	static int started = 0;
-	pthread_t th;
-	if (started) return;
-	started = 1;
-	if (pthread_create(&th, NULL, warmup_fn, NULL) == 0) pthread_detach(th);
+	if (g_warm_state) return;
+	if (pthread_create(&g_warm_thread, NULL, warmup_fn, NULL) == 0) g_warm_state = 1;
+	else g_warm_state = 2;
+}
+/* before exit(): never tear the process down while the CUDA start-up is still in flight on the other thread */
+void tdg_shim_warmup_join(void)
+{
+	if (g_warm_state == 1) { pthread_join(g_warm_thread, NULL); g_warm_state = 2; }
 }
 
 /* FNV-1a over the flattened tables: a model_bag is rebuilt (same pointer or not) whenever the

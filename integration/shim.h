@@ -8,6 +8,7 @@ struct model_bag;
 tdg_context* tdg_shim_context(struct parameters* param);
 /* start creating the GPU context on a background thread (hides the CUDA start-up behind host set-up) */
 void tdg_shim_warmup(void);
+void tdg_shim_warmup_join(void);   /* call before exit() / at the end of the controller */
 /* struct model_bag -> tdg_model through a small content-keyed cache; seg types come from param->read_structure */
 tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param);
 /* same tables, scratch sized for reads up to max_len (the tables do not depend on the read length) */
