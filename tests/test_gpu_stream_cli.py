@@ -197,3 +197,21 @@ def test_streaming_on_two_devices_matches_one(tmp_path):
     assert len(outs[0]) == 25 and [os.path.basename(x) for x in outs[0]] == [os.path.basename(x) for x in outs[1]]
     for a, b in zip(*outs):
         assert fc.cmp(a, b, shallow=False), os.path.basename(a)
+
+
+def test_existing_output_files_are_refused_like_the_reference(tmp_path):
+    """Second run into the same prefix: the reference refuses (check_for_existing_demultiplexed_files_multiple,
+    barcode_hmm.c:150-158); so does the streaming controller, and the first run's files stay untouched."""
+    tmp = str(tmp_path)
+    make_fastq(os.path.join(tmp, "in.fq"), 1500, [("B", TAGS), ("R", None)], seed=21)
+    files = run_pair(tmp, f"-1 {BARC} -2 R:N in.fq")
+    before = {f: open(f, "rb").read() for f in files}
+    msgs = {}
+    for tag, binary in (("cpu", os.path.join(REF, "tagdust_rtest")), ("gpu", GPU_BIN)):
+        r = subprocess.run(f"{binary} -seed 42 -t 4 -1 {BARC} -2 R:N in.fq -o {tmp}/{tag}/out", cwd=tmp, shell=True, capture_output=True, text=True)
+        msgs[tag] = (r.returncode, "already exists" in (r.stdout + r.stderr))
+    assert msgs["cpu"] == msgs["gpu"] and msgs["gpu"][1]
+    gpu_files = sorted(glob.glob(os.path.join(tmp, "gpu", "out*.fq")))
+    cpu_files = sorted(glob.glob(os.path.join(tmp, "cpu", "out*.fq")))
+    for a, b in zip(cpu_files, gpu_files):
+        assert open(a, "rb").read() == open(b, "rb").read() == before[a]
