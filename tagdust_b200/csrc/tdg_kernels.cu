@@ -15,6 +15,10 @@
 //   k_label    : exp() of the posterior matrix, constrained label DP, traceback, extraction
 // The 16 000-entry logsum table and the compiled architecture live in shared memory.
 // Terms whose transition is log(0) are never evaluated: logsum(x, -inf) == x exactly.
+// Per segment the host picks one of three code paths (tdg_host.cu: derive_model):
+//   KIND 1, 3..16 columns  standard B/F/S pattern, fully unrolled, columns in registers, five scalar transitions
+//   KIND 0, 1..8 columns   any pattern (P/O/G/R, 1-2 column HMMs), unrolled with run-time live masks
+//   column loop            longer segments; profile state in shared memory when it fits, else thread-local
 //
 // Compiled with -fmad=false: the reference binary contains no fused multiply-adds.
 #include <cuda_runtime.h>
