@@ -215,3 +215,37 @@ def test_existing_output_files_are_refused_like_the_reference(tmp_path):
     cpu_files = sorted(glob.glob(os.path.join(tmp, "cpu", "out*.fq")))
     for a, b in zip(cpu_files, gpu_files):
         assert open(a, "rb").read() == open(b, "rb").read() == before[a]
+
+
+def test_reads_longer_than_announced_grow_model_and_batches(tmp_path, gpu_ctx):
+    """A file whose later reads are longer than what the set-up announced (get_sequence_stats only looks at the
+    first million reads): the pipeline re-sizes the staging batch of that slot and the model's scratch layout
+    (the reference re-allocates its model_bag, barcode_hmm.c:293-309) and writes the same bytes as a run that
+    knew the lengths from the start."""
+    import filecmp as fc
+    from refharness import background_logp
+    from tagdust_b200 import stream
+    from tagdust_b200.api import compile_architecture
+    tags = TAGS
+    desc = compile_architecture([BARC, "R:N"], background_logp((2.5e6, 2.5e6, 2.5e6, 2.5e6, 1.0)), 60.0, 150)
+    rng = np.random.default_rng(5)
+    fq = str(tmp_path / "grow.fq")
+    with open(fq, "w") as fh:
+        for r in range(6000):
+            L = 44 if r < 2500 else int(rng.integers(60, 131))
+            seq = tags[r % len(tags)] + "".join(rng.choice(list("ACGT"), size=L))
+            fh.write(f"@g{r}\n{seq}\n+\n{'F' * len(seq)}\n")
+    outs = []
+    for announced, model_len in ((50, 60), (136, 146)):
+        model = gpu_ctx.model(desc, model_len)
+        d = tmp_path / f"run{announced}"
+        d.mkdir()
+        st = stream.demux_run(gpu_ctx, [dict(path=fq, model=model, num_read_segments=1, threshold=1.0, max_seq_len=announced,
+                                             expected_len=announced)], str(d / "out"), barcode_input=0, barcode_names=list(tags),
+                              threads=4, chunk_reads=800)
+        assert st["total_read"] == 6000
+        outs.append(sorted(glob.glob(str(d / "out*.fq"))))
+        model.close()
+    assert len(outs[0]) == len(tags) + 1
+    for a, b in zip(*outs):
+        assert fc.cmp(a, b, shallow=False), os.path.basename(a)
