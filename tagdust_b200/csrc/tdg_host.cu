@@ -287,6 +287,7 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 		SegInfo& g = hm.seg[s];
 		g.ta = g.tb = g.tb2 = g.tc = g.td = 0.0f;
 		if (g.nc < 3) continue;  // up to kMaxStdCols columns the kernels are fully unrolled, beyond that they loop over the columns
+		if (getenv("TDG_NO_STDU")) continue;  // tests: every segment through the generic (run-time mask) paths
 		const float* r0 = rec + (size_t)g.colbase * kColRec;
 		const float* e0 = emit + (size_t)g.colbase * kEmitRec;
 		const float ta = r0[F_MM], tb = r0[F_MI], tc = r0[F_II], td = r0[F_IM];
@@ -354,6 +355,7 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 			else { hm.dp_src[(size_t)j * kMaxSources + k++] = c; c++; }
 		}
 	}
+	if (getenv("TDG_GENERIC_LABEL_DP")) hm.dp_structured = 0;  // tests: the verbatim O(L*H^2) label DP
 	for (int k = 0; k < 5; k++) hm.bg[k] = d->background[k];
 	// random model constants (barcode_hmm.c:4520,4523): float argument, double log, float result
 	hm.r_step = p2s((float)(1.0 - (1.0 / (float)d->average_raw_length)));

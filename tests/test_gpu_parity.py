@@ -264,3 +264,22 @@ def test_small_waves_and_long_reads(gpu_ctx, oracle, ref, monkeypatch):
 def synth_encode(s):
     from tagdust_b200.synth import encode
     return encode(s)
+
+
+@pytest.mark.parametrize("env", ["TDG_GENERIC_LABEL_DP", "TDG_NO_STDU", "TDG_NO_SMEM_STATE"])
+@pytest.mark.parametrize("name", ["b48_r", "f_s_b_r", "b_b_r", "o_b_s_r", "s20_b_r", "f12_b12_r", "p18_b_r_p14"])
+def test_alternative_kernel_paths_give_the_same_bits(gpu_ctx, oracle, ref, name, env, monkeypatch):
+    """Every read must come out the same whichever code path the host picks: the verbatim O(L*H^2) label DP
+    instead of the structured one, the generic run-time-mask columns instead of the standard-pattern ones,
+    thread-local instead of shared-memory profile state."""
+    n = 600
+    codes, lens, _ = make_case_reads(name, n, seed=5)
+    p, mb, desc = build_ref_model(ref, name)
+    kw = dict(threshold=1.5, minlen=16, dust=100)
+    ora = oracle.run(desc, MODE_GET_LABEL, codes, lens, threads=8, **kw)
+    monkeypatch.setenv(env, "1")
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, **kw)
+    monkeypatch.delenv(env)
+    rep = compare(gpu, ora, lens, MODE_GET_LABEL, name)
+    ref.model_free(mb); ref.param_free(p)
+    assert all(v == 0 for v in rep.values()), f"{name} with {env}: mismatches {rep}"
