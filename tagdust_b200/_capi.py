@@ -213,7 +213,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("TDG_LIB") or LIB_PATH   # TDG_LIB: A/B runs of two builds on the same box
     if not os.path.exists(p):
         raise OSError(
             f"{p} not found: build the CUDA library first "
