@@ -42,7 +42,10 @@ constexpr int TDG_MAX_HMMS_DEV = 255;
 // in its mantissa (0 <= x < 2^23), so its bit pattern << 2 plus a pre-offset shared-memory
 // base is the byte address of tab[(int)x]; no F2I (XU pipe) on the hot path.
 // ------------------------------------------------------------------------------------------
-constexpr int kPrefetchDist = 5;
+#ifndef TDG_PREFETCH_DIST
+#define TDG_PREFETCH_DIST 5
+#endif
+constexpr int kPrefetchDist = TDG_PREFETCH_DIST;  // 0 = no L1 prefetch of the silent-state lines
 #ifndef TDG_AHEAD
 #define TDG_AHEAD 1
 #endif
@@ -320,7 +323,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 				cs_q[kAhead - 1] = ld_keep(csp - (size_t)kAhead * kBlock, keep);
 				if (!last_seg) ps_q[kAhead - 1] = ld_keep(psp - (size_t)kAhead * kBlock, keep);
 			}
-			if (i > kPrefetchDist) {  // pull the silent-state lines of iteration i-kPrefetchDist towards L1
+			if (kPrefetchDist > 0 && i > kPrefetchDist) {  // pull the silent-state lines of iteration i-kPrefetchDist towards L1
 				prefetch_l1(csp - (size_t)kPrefetchDist * kBlock);
 				if (!last_seg) prefetch_l1(psp - (size_t)kPrefetchDist * kBlock);
 			}
