@@ -228,7 +228,7 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import torch
     from tagdust_b200 import dist_util
-    from tagdust_b200.api import MODE_GET_LABEL, Context, compile_architecture
+    from tagdust_b200.api import MODE_GET_LABEL, Context, compile_architecture, live_ops
 
     rank, world, local = dist_util.env_rank()
     if not torch.cuda.is_available():
@@ -315,9 +315,13 @@ def run_gpu_arm(args):
     fp32_peak = 148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12   # T lane-ops/s
     dom = max(prof, key=lambda k: prof[k]["ms"])
     ops_colpos = {"k_backward": OPS_PER_COLPOS_BWD, "k_forward": OPS_PER_COLPOS_FWD, "k_label": 0}
-    dom_ops = n_reads * args.steps * READ_LEN * C * ops_colpos[dom]
+    # live work: the logsums / adds the kernels execute (log(0) terms are skipped exactly), from the compiled model;
+    # a logsum is costed at SURVEY 8d's 9 FP32-pipe ops
+    lo = live_ops(desc)
+    live_pos = {"k_backward": 9 * lo["ls_bwd"] + lo["add_bwd"], "k_forward": 9 * lo["ls_fwd"] + lo["add_fwd"], "k_label": 0.0}
     dom_s = prof[dom]["ms"] / 1000.0
-    achieved = dom_ops / dom_s / 1e12 if dom_s > 0 else 0.0
+    achieved_alg = n_reads * args.steps * READ_LEN * C * ops_colpos[dom] / dom_s / 1e12 if dom_s > 0 else 0.0
+    achieved = n_reads * args.steps * READ_LEN * live_pos[dom] / dom_s / 1e12 if dom_s > 0 else 0.0
     # algorithmic HBM bytes of the backward->forward hand-off: Mb,Ib of every (column, position), written once, read once
     hbm_bytes = n_reads * args.steps * READ_LEN * C * 8 * 2
     line = {
@@ -336,10 +340,16 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "roofline": {"bound": "fp32", "kernel": dom, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak, "traffic": None,
-                     "ops_per_column_position": ops_colpos[dom],
+                     "achieved_algorithmic": achieved_alg, "frac_algorithmic": achieved_alg / fp32_peak,
+                     "live_ops_per_hmm_position": live_pos[dom] / desc.total_hmms,
+                     "live_logsums_per_hmm_position": (lo["ls_fwd"] if dom == "k_forward" else lo["ls_bwd"]) / desc.total_hmms,
+                     "ops_per_column_position_algorithmic": ops_colpos[dom],
                      "peak_source": f"148 SM x 128 FP32 lanes x sm_max_mhz, {pk_src}",
-                     "note": "algorithmic FP32-pipe ops (SURVEY 8d); T lane-ops/s reported in the TFLOP/s unit"},
-        "roofline_whole_path": {"achieved": value / world * READ_LEN * C * (OPS_PER_COLPOS_BWD + OPS_PER_COLPOS_FWD) / 1e12,
+                     "note": "frac = LIVE FP32-pipe ops (logsums and adds the kernel executes; a logsum = 9 ops as in SURVEY 8d) "
+                             "/ duration / lane peak; frac_algorithmic counts SURVEY 8d's 8+10 logsums per (column, position) "
+                             "including the log(0) terms that are never evaluated, so it can exceed 1; T lane-ops/s in the TFLOP/s unit"},
+        "roofline_whole_path": {"achieved": value / world * READ_LEN * (live_pos["k_backward"] + live_pos["k_forward"]) / 1e12,
+                                "achieved_algorithmic": value / world * READ_LEN * C * (OPS_PER_COLPOS_BWD + OPS_PER_COLPOS_FWD) / 1e12,
                                 "peak": fp32_peak, "unit": "TFLOP/s"},
         "hbm": {"achieved_gbs": hbm_bytes / ((prof["k_backward"]["ms"] + prof["k_forward"]["ms"]) / 1000.0) / 1e9,
                 "peak_gbs": pk.get("hbm_gbs"), "what": "Mb/Ib scratch write+read over k_backward+k_forward time"},
@@ -348,10 +358,14 @@ def run_gpu_arm(args):
                   "read_type_counts": tallies.tolist()},
     }
     line["roofline_whole_path"]["frac"] = line["roofline_whole_path"]["achieved"] / fp32_peak
+    line["roofline_whole_path"]["frac_algorithmic"] = line["roofline_whole_path"]["achieved_algorithmic"] / fp32_peak
+    if not os.environ.get("TDG_LIB"):   # experiment builds (scripts/build_variant.sh) may skip work on purpose
+        assert line["roofline"]["frac"] <= 1.0 and line["roofline_whole_path"]["frac"] <= 1.0, "live-op roofline fraction above 1"
     traffic, traffic_src, ncu_k = ncu_traffic(dom)
     line["roofline"]["traffic"] = traffic
     line["roofline"]["traffic_source"] = traffic_src
-    for key in ("issue_active_pct", "lsu_wavefronts_pct"):   # ncu: what the kernel is actually bound by per SM
+    for key in ("issue_active_pct", "lsu_wavefronts_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_lsu_pct",
+                "shared_bank_conflict_share"):   # ncu: what the kernel is actually bound by per SM
         if key in ncu_k:
             line["roofline"][key] = ncu_k[key]
     # the same kernel against the HBM roofline: algorithmic bytes = Mb/Ib of every stored (column, position), moved once

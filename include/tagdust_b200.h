@@ -201,6 +201,12 @@ int  tdg_batch_download(tdg_batch* b, tdg_result* out);
 int  tdg_profile_enable(tdg_context* ctx, int on);
 int  tdg_profile_read(tdg_context* ctx, int device_index, float ms[3], int launches[3]);
 
+/* Work the kernels execute per read position, summed over all HMMs of the model (host-only, no GPU needed):
+ * out[0] logsums and out[1] float adds of the backward pass, out[2] / out[3] the same for forward + posterior.
+ * Terms whose transition is log(0) are never evaluated (logsum(x, -inf) == x), so these "live" counts are lower
+ * than SURVEY 8d's algorithmic 8 + 10 logsums per (column, position); bench.py's roofline.frac uses them. */
+int  tdg_desc_live_ops(const tdg_model_desc* desc, double out[4]);
+
 /* work accounting for the roofline: profile-column cells (2*L*C per read) */
 double tdg_batch_cells(const tdg_model* m, const tdg_batch* b);
 

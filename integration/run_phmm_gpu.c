@@ -33,8 +33,11 @@ static tdg_context* g_ctx = NULL;
 static tdg_batch* g_batch = NULL;
 static int g_batch_reads = 0, g_batch_len = 0;
 
+/* Content-keyed model cache.  A hit is only accepted after a memcmp of the whole flattened table blob
+ * (the FNV key alone could collide); entries are evicted round robin, never while a caller holds them:
+ * the arch-comparison path builds its models uncached (up to MAX_NUM_ARCH of them are alive at once). */
 #define MODEL_CACHE 24
-static struct { unsigned long long key; int max_len; tdg_model* m; } g_models[MODEL_CACHE];
+static struct { unsigned long long key; int max_len; size_t blob_n; unsigned char* blob; tdg_model* m; } g_models[MODEL_CACHE];
 static int g_model_next = 0;
 
 static int fail_msg(struct parameters* param, const char* what)
@@ -98,8 +101,100 @@ tdg_context* tdg_shim_context(struct parameters* param)
 	return ensure_ctx(param) == kslOK ? g_ctx : NULL;
 }
 
-/* struct model_bag -> tdg_model (flatten in segment -> hmm -> column order) */
-static tdg_model* get_model_len(struct model_bag* mb, struct parameters* param, int want_len);
+/* struct model_bag -> flat tables (segment -> hmm -> column order), all in one allocation */
+struct flat_model {
+	int S, H, C;
+	unsigned char* blob; size_t blob_n;   /* everything below points into blob */
+	char* seg_type; int32_t* nh; int32_t* nc; float* skip; float* bg; float* tr; float* me; float* ie; float* sM; float* sI;
+	int32_t* label; float* T; int32_t* avg;
+};
+
+static int flatten_model(struct model_bag* mb, struct parameters* param, struct flat_model* fm)
+{
+	int S = mb->num_models, H = mb->total_hmm_num, C = 0, j, f, g, k, c = 0;
+	size_t o = 0;
+	for (j = 0; j < S; j++) C += mb->model[j]->num_hmms * mb->model[j]->hmms[0]->num_columns;
+	fm->S = S; fm->H = H; fm->C = C;
+#define TAKE(T, n) (o = (o + 7) & ~(size_t)7, o += sizeof(T) * (size_t)(n), o - sizeof(T) * (size_t)(n))
+	const size_t o_nh = TAKE(int32_t, S), o_nc = TAKE(int32_t, S), o_skip = TAKE(float, S), o_bg = TAKE(float, 5),
+	             o_tr = TAKE(float, C * 9), o_me = TAKE(float, C * 5), o_ie = TAKE(float, C * 5), o_sM = TAKE(float, C),
+	             o_sI = TAKE(float, C), o_label = TAKE(int32_t, H), o_T = TAKE(float, (size_t)H * H), o_avg = TAKE(int32_t, 1),
+	             o_type = TAKE(char, S + 1);
+#undef TAKE
+	fm->blob_n = o;
+	fm->blob = calloc(1, o);   /* zeroed: alignment gaps take part in the hash / memcmp */
+	if (!fm->blob) return kslEMEM;
+	fm->nh = (int32_t*)(fm->blob + o_nh); fm->nc = (int32_t*)(fm->blob + o_nc); fm->skip = (float*)(fm->blob + o_skip);
+	fm->bg = (float*)(fm->blob + o_bg); fm->tr = (float*)(fm->blob + o_tr); fm->me = (float*)(fm->blob + o_me);
+	fm->ie = (float*)(fm->blob + o_ie); fm->sM = (float*)(fm->blob + o_sM); fm->sI = (float*)(fm->blob + o_sI);
+	fm->label = (int32_t*)(fm->blob + o_label); fm->T = (float*)(fm->blob + o_T); fm->avg = (int32_t*)(fm->blob + o_avg);
+	fm->seg_type = (char*)(fm->blob + o_type);
+	for (k = 0; k < 5; k++) fm->bg[k] = mb->model[0]->background_nuc_frequency[k];
+	for (j = 0; j < S; j++) {
+		struct model* m = mb->model[j];
+		fm->seg_type[j] = param->read_structure->type[j];
+		fm->nh[j] = m->num_hmms; fm->nc[j] = m->hmms[0]->num_columns; fm->skip[j] = m->skip;
+		for (f = 0; f < m->num_hmms; f++)
+			for (g = 0; g < m->hmms[f]->num_columns; g++) {
+				struct hmm_column* col = m->hmms[f]->hmm_column[g];
+				for (k = 0; k < 9; k++) fm->tr[c * 9 + k] = col->transition[k];
+				for (k = 0; k < 5; k++) { fm->me[c * 5 + k] = col->m_emit[k]; fm->ie[c * 5 + k] = col->i_emit[k]; }
+				fm->sM[c] = m->silent_to_M[f][g]; fm->sI[c] = m->silent_to_I[f][g];
+				c++;
+			}
+	}
+	for (j = 0; j < H; j++) { fm->label[j] = mb->label[j]; for (k = 0; k < H; k++) fm->T[j * H + k] = mb->transition_matrix[j][k]; }
+	*fm->avg = mb->average_raw_length;
+	return kslOK;
+}
+
+static tdg_model* create_from_flat(const struct flat_model* fm, int max_len)
+{
+	tdg_model_desc d;
+	tdg_model* out = NULL;
+	d.num_segments = fm->S; d.total_hmms = fm->H; d.total_columns = fm->C; d.average_raw_length = *fm->avg;
+	d.seg_type = fm->seg_type; d.seg_num_hmms = fm->nh; d.seg_num_cols = fm->nc; d.seg_skip = fm->skip; d.background = fm->bg;
+	d.transition = fm->tr; d.m_emit = fm->me; d.i_emit = fm->ie; d.silent_to_M = fm->sM; d.silent_to_I = fm->sI; d.label = fm->label;
+	d.transition_matrix = fm->T;
+	if (tdg_model_create(g_ctx, &d, max_len, &out) != TDG_OK) return NULL;
+	return out;
+}
+
+/* uncached: the caller owns the model and destroys it (arch comparison: all models of ab->archs[] are alive at once) */
+static tdg_model* build_model_uncached(struct model_bag* mb, struct parameters* param, int max_len)
+{
+	struct flat_model fm;
+	tdg_model* out;
+	if (ensure_ctx(param) != kslOK) return NULL;
+	if (flatten_model(mb, param, &fm) != kslOK) return NULL;
+	out = create_from_flat(&fm, max_len);
+	free(fm.blob);
+	return out;
+}
+
+static tdg_model* get_model_len(struct model_bag* mb, struct parameters* param, int want_len)
+{
+	struct flat_model fm;
+	int k;
+	if (ensure_ctx(param) != kslOK) return NULL;
+	if (flatten_model(mb, param, &fm) != kslOK) return NULL;
+	const int max_len = want_len;
+	const unsigned long long key = fnv(1469598103934665603ULL, fm.blob, fm.blob_n);
+	tdg_model* out = NULL;
+	for (k = 0; k < MODEL_CACHE && !out; k++)
+		/* same tables AND same length: a model sized for the long calibration reads would make every
+		 * wave of the real run smaller (scratch per read grows with max_len) */
+		if (g_models[k].m && g_models[k].key == key && g_models[k].max_len == max_len && g_models[k].blob_n == fm.blob_n &&
+		    memcmp(g_models[k].blob, fm.blob, fm.blob_n) == 0) out = g_models[k].m;
+	if (out) { free(fm.blob); return out; }
+	out = create_from_flat(&fm, max_len);
+	if (!out) { free(fm.blob); return NULL; }
+	if (g_models[g_model_next].m) { tdg_model_destroy(g_models[g_model_next].m); free(g_models[g_model_next].blob); }
+	g_models[g_model_next].m = out; g_models[g_model_next].key = key; g_models[g_model_next].max_len = max_len;
+	g_models[g_model_next].blob = fm.blob; g_models[g_model_next].blob_n = fm.blob_n;
+	g_model_next = (g_model_next + 1) % MODEL_CACHE;
+	return out;
+}
 
 tdg_model* tdg_shim_get_model_len(struct model_bag* mb, struct parameters* param, int max_len)
 {
@@ -109,62 +204,6 @@ tdg_model* tdg_shim_get_model_len(struct model_bag* mb, struct parameters* param
 tdg_model* tdg_shim_get_model(struct model_bag* mb, struct parameters* param)
 {
 	return get_model_len(mb, param, mb->current_dyn_length);   /* >= max_seq_len + 10 (barcode_hmm.c:5778) */
-}
-
-static tdg_model* get_model_len(struct model_bag* mb, struct parameters* param, int want_len)
-{
-	if (ensure_ctx(param) != kslOK) return NULL;
-	int S = mb->num_models, H = mb->total_hmm_num, C = 0, j, f, g, k, c = 0;
-	for (j = 0; j < S; j++) C += mb->model[j]->num_hmms * mb->model[j]->hmms[0]->num_columns;
-	char* seg_type = malloc(S + 1);
-	int32_t* nh = malloc(sizeof(int32_t) * S); int32_t* nc = malloc(sizeof(int32_t) * S);
-	float* skip = malloc(sizeof(float) * S);
-	float bg[5];
-	float* tr = malloc(sizeof(float) * C * 9); float* me = malloc(sizeof(float) * C * 5); float* ie = malloc(sizeof(float) * C * 5);
-	float* sM = malloc(sizeof(float) * C); float* sI = malloc(sizeof(float) * C);
-	int32_t* label = malloc(sizeof(int32_t) * H); float* T = malloc(sizeof(float) * H * H);
-	for (k = 0; k < 5; k++) bg[k] = mb->model[0]->background_nuc_frequency[k];
-	for (j = 0; j < S; j++) {
-		struct model* m = mb->model[j];
-		seg_type[j] = param->read_structure->type[j];
-		nh[j] = m->num_hmms; nc[j] = m->hmms[0]->num_columns; skip[j] = m->skip;
-		for (f = 0; f < m->num_hmms; f++)
-			for (g = 0; g < m->hmms[f]->num_columns; g++) {
-				struct hmm_column* col = m->hmms[f]->hmm_column[g];
-				for (k = 0; k < 9; k++) tr[c * 9 + k] = col->transition[k];
-				for (k = 0; k < 5; k++) { me[c * 5 + k] = col->m_emit[k]; ie[c * 5 + k] = col->i_emit[k]; }
-				sM[c] = m->silent_to_M[f][g]; sI[c] = m->silent_to_I[f][g];
-				c++;
-			}
-	}
-	seg_type[S] = 0;
-	for (j = 0; j < H; j++) { label[j] = mb->label[j]; for (k = 0; k < H; k++) T[j * H + k] = mb->transition_matrix[j][k]; }
-	const int max_len = want_len;
-	unsigned long long key = 1469598103934665603ULL;
-	key = fnv(key, seg_type, S); key = fnv(key, nh, 4 * S); key = fnv(key, nc, 4 * S); key = fnv(key, skip, 4 * S);
-	key = fnv(key, bg, 20); key = fnv(key, tr, 4 * C * 9); key = fnv(key, me, 4 * C * 5); key = fnv(key, ie, 4 * C * 5);
-	key = fnv(key, sM, 4 * C); key = fnv(key, sI, 4 * C); key = fnv(key, label, 4 * H); key = fnv(key, T, 4 * H * H);
-	key = fnv(key, &mb->average_raw_length, sizeof(int));
-	tdg_model* out = NULL;
-	for (k = 0; k < MODEL_CACHE; k++)
-		/* same tables AND same length: a model sized for the long calibration reads would make every
-		 * wave of the real run smaller (scratch per read grows with max_len) */
-		if (g_models[k].m && g_models[k].key == key && g_models[k].max_len == max_len) out = g_models[k].m;
-	if (!out) {
-		tdg_model_desc d;
-		d.num_segments = S; d.total_hmms = H; d.total_columns = C; d.average_raw_length = mb->average_raw_length;
-		d.seg_type = seg_type; d.seg_num_hmms = nh; d.seg_num_cols = nc; d.seg_skip = skip; d.background = bg;
-		d.transition = tr; d.m_emit = me; d.i_emit = ie; d.silent_to_M = sM; d.silent_to_I = sI; d.label = label;
-		d.transition_matrix = T;
-		if (tdg_model_create(g_ctx, &d, max_len, &out) != TDG_OK) out = NULL;
-		else {
-			if (g_models[g_model_next].m) tdg_model_destroy(g_models[g_model_next].m);
-			g_models[g_model_next].m = out; g_models[g_model_next].key = key; g_models[g_model_next].max_len = max_len;
-			g_model_next = (g_model_next + 1) % MODEL_CACHE;
-		}
-	}
-	free(seg_type); free(nh); free(nc); free(skip); free(tr); free(me); free(ie); free(sM); free(sI); free(label); free(T);
-	return out;
 }
 
 static int ensure_batch(struct parameters* param, int numseq, int max_len)
@@ -230,23 +269,23 @@ static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_
 
 	if (mode == MODE_ARCH_COMP) {
 		if (!ab) return kslFAIL;
-		tdg_model** models = malloc(sizeof(tdg_model*) * ab->num_arch);
-		int max_len = 0;
-		for (i = 0; i < ab->num_arch; i++) {
-			models[i] = tdg_shim_get_model(ab->archs[i], param);   /* NB: seg types come from param->read_structure; only
-			                                                 needed by extraction, not by backward() */
-			if (!models[i]) { free(models); return fail_msg(param, "tdg_model_create"); }
-			if (ab->archs[i]->current_dyn_length > max_len) max_len = ab->archs[i]->current_dyn_length;
-		}
-		if (load_batch(param, ri, numseq, 1) != kslOK) { free(models); return kslFAIL; }
+		tdg_model** models = calloc(ab->num_arch, sizeof(tdg_model*));
 		float* post = malloc(sizeof(float) * ab->num_arch);
-		if (tdg_arch_compare(g_ctx, models, ab->num_arch, g_batch, param->num_threads, NULL, post) != TDG_OK) {
-			free(models); free(post);
-			return fail_msg(param, "tdg_arch_compare");
+		int rc = kslOK;
+		/* uncached, owned here: test_architectures allows up to MAX_NUM_ARCH (100) candidates, all alive until
+		 * tdg_arch_compare returns -- more than the cache holds */
+		for (i = 0; i < ab->num_arch && rc == kslOK; i++) {
+			models[i] = build_model_uncached(ab->archs[i], param, ab->archs[i]->current_dyn_length);   /* NB: seg types come from
+			                                                 param->read_structure; only needed by extraction, not by backward() */
+			if (!models[i]) rc = fail_msg(param, "tdg_model_create");
 		}
-		for (i = 0; i < ab->num_arch; i++) ab->arch_posterior[i] = post[i];
+		if (rc == kslOK && load_batch(param, ri, numseq, 1) != kslOK) rc = kslFAIL;
+		if (rc == kslOK && tdg_arch_compare(g_ctx, models, ab->num_arch, g_batch, param->num_threads, NULL, post) != TDG_OK)
+			rc = fail_msg(param, "tdg_arch_compare");
+		if (rc == kslOK) for (i = 0; i < ab->num_arch; i++) ab->arch_posterior[i] = post[i];
+		for (i = 0; i < ab->num_arch; i++) if (models[i]) tdg_model_destroy(models[i]);
 		free(models); free(post);
-		return kslOK;
+		return rc;
 	}
 	if (mode != MODE_GET_LABEL && mode != MODE_GET_PROB) return kslFAIL; /* MODE_TRAIN: no live caller */
 

@@ -126,6 +126,7 @@ PROTOTYPES = {
     "tdg_decode_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RunParamsC), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "tdg_batch_download": (C.c_int, [C.c_void_p, C.POINTER(ResultC)]),
     "tdg_batch_cells": (C.c_double, [C.c_void_p, C.c_void_p]),
+    "tdg_desc_live_ops": (C.c_int, [C.POINTER(ModelDescC), C.POINTER(C.c_double)]),
     "tdg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "tdg_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }

@@ -54,6 +54,15 @@ def compile_architecture(segments, background_logp, average_length, max_seq_len,
         lib.tdg_arch_destroy(h)
 
 
+def live_ops(desc: ModelDesc):
+    """tdg_desc_live_ops: logsums / adds the kernels execute per read position over all HMMs
+    (dead log(0) terms excluded) -> dict(ls_bwd, add_bwd, ls_fwd, add_fwd)."""
+    lib = _capi.load_library()
+    out = (C.c_double * 4)()
+    _check(lib, lib.tdg_desc_live_ops(C.byref(desc.c), out))
+    return dict(ls_bwd=out[0], add_bwd=out[1], ls_fwd=out[2], add_fwd=out[3])
+
+
 class Model:
     def __init__(self, ctx, desc: ModelDesc, max_len: int):
         self.ctx, self.desc, self.max_len = ctx, desc, int(max_len)

@@ -9,7 +9,7 @@
 //   set_hmm_transition_parameters            barcode_hmm.c:1710-1881
 //   gaussian_pdf                             misc.c:375-379
 //   the calibration edit                     calibrateQ.c:67-86
-// tests/test_arch_compile.py compares its output bit-for-bit with the reference's own
+// tests/test_capi_host.py (test_arch_compile_*) compares its output bit-for-bit with the reference's own
 // init_model_bag (oracle/_ref) over every segment type.
 #include <cmath>
 #include <cstdio>

@@ -9,7 +9,10 @@ namespace tdg {
 constexpr int kMaxSegments = 16;
 constexpr int kLogsumSize = 16000;
 // Decode kernels: one CTA per SM, kBlock reads in flight per CTA (thread-per-read).
-constexpr int kBlock = 512;
+#ifndef TDG_BLOCK
+#define TDG_BLOCK 512
+#endif
+constexpr int kBlock = TDG_BLOCK;  // experiments: 256 with two co-resident CTAs per SM (TDG_LANES=2)
 // Label-DP kernel uses smaller CTAs (no 64 KB table in shared memory).
 constexpr int kDpBlock = 128;
 constexpr int kColRec = 12;    // floats per column record (3 x float4)

@@ -93,6 +93,10 @@ struct DeviceCtx {
 	size_t scratch_bytes = 0;
 	size_t smem_optin = 0;
 	int configured_smem = 0;
+	// experiment (TDG_LANES=2): waves alternate between `compute` and `lane2`, each with its own scratch half, so that
+	// the HBM-bound k_backward of one wave shares the SMs with the issue-bound k_forward of another
+	cudaStream_t lane2 = nullptr;
+	cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
 	// optional per-kernel timing (tdg_profile_*): event pairs recorded around every launch
 	bool profile = false;
 	std::vector<cudaEvent_t> ev[3];  // [kernel kind] start/stop pairs
@@ -119,25 +123,35 @@ extern "C" int tdg_init(int n_devices, const int* device_ids, tdg_context** out)
 	if (n_devices > count && !device_ids) return fail(TDG_EINVAL, "asked for %d devices, %d visible", n_devices, count);
 	init_tab();
 	auto* ctx = new tdg_context();
-	for (int k = 0; k < n_devices; k++) {
+	// every device that got as far as push_back is released by tdg_shutdown on a later failure
+	auto init_dev = [&](int k) -> int {
 		DeviceCtx d;
 		d.dev = device_ids ? device_ids[k] : k;
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, d.dev));
-		if (prop.major < 10) {
-			delete ctx;
+		if (prop.major < 10)
 			return fail(TDG_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", d.dev, prop.major, prop.minor);
-		}
 		CK(cudaSetDevice(d.dev));
 		d.sms = prop.multiProcessorCount;
 		d.ctas = d.sms;
 		d.smem_optin = prop.sharedMemPerBlockOptin;
 		CK(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
-		CK(cudaMalloc(&d.d_tab, sizeof g_tab));
+		ctx->devs.push_back(d);
+		DeviceCtx& dd = ctx->devs.back();
+		CK(cudaMalloc(&dd.d_tab, sizeof g_tab));
 		std::vector<float> t(g_tab, g_tab + kLogsumSize);
 		for (int i = 15700; i < kLogsumSize; i++) t[i] = 0.0f;  // see LS() in tdg_kernels.cu
-		CK(cudaMemcpy(d.d_tab, t.data(), sizeof g_tab, cudaMemcpyHostToDevice));
-		ctx->devs.push_back(d);
+		CK(cudaMemcpy(dd.d_tab, t.data(), sizeof g_tab, cudaMemcpyHostToDevice));
+		return TDG_OK;
+	};
+	for (int k = 0; k < n_devices; k++) {
+		const int rc = init_dev(k);
+		if (rc != TDG_OK) {
+			const std::string keep = g_err;
+			tdg_shutdown(ctx);
+			g_err = keep;
+			return rc;
+		}
 	}
 	*out = ctx;
 	return TDG_OK;
@@ -152,6 +166,7 @@ extern "C" void tdg_shutdown(tdg_context* ctx)
 		if (d.scratch) cudaFree(d.scratch);
 		if (d.d_tab) cudaFree(d.d_tab);
 		for (int k = 0; k < 3; k++) for (auto e : d.ev[k]) cudaEventDestroy(e);
+		if (d.lane2) { cudaStreamSynchronize(d.lane2); cudaStreamDestroy(d.lane2); cudaEventDestroy(d.lane_fork); cudaEventDestroy(d.lane_join); }
 		cudaStreamDestroy(d.compute);
 	}
 	delete ctx;
@@ -199,6 +214,12 @@ extern "C" int tdg_profile_read(tdg_context* ctx, int devk, float ms[3], int lau
 	return TDG_OK;
 }
 
+static int num_lanes()
+{
+	static const int v = [] { const char* e = getenv("TDG_LANES"); const int n = e ? atoi(e) : 1; return n == 2 ? 2 : 1; }();
+	return v;
+}
+
 static int ensure_scratch(DeviceCtx& d, size_t bytes)
 {
 	if (bytes <= d.scratch_bytes) return TDG_OK;
@@ -237,6 +258,8 @@ struct HostModel {  // derived, GPU independent
 	float r_step = 0, r_end = 0;
 	int dead_terms = 0, std_segments = 0;
 	int loop_cols = 0;   // longest segment that runs a column-loop kernel path (0 = every segment is unrolled)
+	// logsums / float adds the kernels execute per read position over all HMMs (dead terms are never evaluated)
+	double live_ls_bwd = 0, live_add_bwd = 0, live_ls_fwd = 0, live_add_fwd = 0;
 };
 
 static bool is_ninf(float v) { return std::isinf(v) && v < 0; }
@@ -316,6 +339,78 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 		const bool unrolled = (g.kind == 1) ? (g.nc >= 3 && g.nc <= kMaxStdCols) : (g.nc <= 8);
 		if (!unrolled) hm.loop_cols = std::max(hm.loop_cols, g.nc);
 	}
+	// Executed work per read position (the roofline's "live" op count): the same term-by-term walk as
+	// bwd_segment / fwd_segment in tdg_kernels.cu, one logsum or add counted where the kernel issues one.
+	for (int s = 0; s < S; s++) {
+		const SegInfo& g = hm.seg[s];
+		for (int f = 0; f < g.nh; f++) {
+			const int c0 = g.colbase + f * g.nc, m = g.nc - 1;
+			auto lv = [&](int col, int field) {
+				uint32_t live;
+				memcpy(&live, &rec[(size_t)(c0 + col) * kColRec + F_LIVE], 4);
+				return (live >> field) & 1u;
+			};
+			double bl = 0, ba = 0, fl = 0, fa = 0;
+			// backward, last column (:3518-3541)
+			if (lv(m, F_MSKIP)) ba += 1;
+			if (lv(m, F_ISKIP)) ba += 1;
+			if (lv(m, F_IM)) { bl += 1; ba += 2; }
+			if (lv(m, F_II)) { bl += 1; ba += 2; }
+			if (lv(m, F_SM)) { bl += 1; ba += 2; }
+			if (lv(m, F_SI)) { bl += 1; ba += 2; }
+			for (int col = m - 1; col >= 0; col--) {  // (:3545-3589)
+				if (lv(col, F_MM)) ba += 2;
+				if (lv(col, F_MSKIP)) { bl += 1; ba += 1; }
+				if (lv(col, F_MI)) { bl += 1; ba += 2; }
+				if (lv(col, F_MD)) { bl += 1; ba += 1; }
+				if (lv(col, F_II)) ba += 2;
+				if (lv(col, F_ISKIP)) { bl += 1; ba += 1; }
+				if (lv(col, F_IM)) { bl += 1; ba += 2; }
+				if (lv(col, F_DD)) ba += 1;
+				if (lv(col, F_DM)) { ba += 2; if (lv(col, F_DD)) bl += 1; }
+				if (lv(col, F_SM)) { bl += 1; ba += 2; }
+				if (lv(col, F_SI)) { bl += 1; ba += 2; }
+			}
+			if (g.skip_live) { bl += 1; ba += 1; }
+			// forward + posterior, column 0 (:4218-4266)
+			{
+				bool have = false;
+				if (lv(0, F_SM)) fa += 2;
+				fa += 2; fl += 1;  // tM, TP
+				if (lv(0, F_SI)) { fa += 1; have = true; }
+				if (lv(0, F_II)) { fa += 1; if (have) fl += 1; have = true; }
+				if (lv(0, F_MI)) { fa += 1; if (have) fl += 1; have = true; }
+				fa += 1;  // + eI
+				if (lv(0, F_SI)) { fl += 1; fa += 4; }
+				fl += 1; fa += 2;  // P
+				if (lv(0, F_MSKIP)) { fl += 1; fa += 1; }
+				if (lv(0, F_ISKIP)) { fl += 1; fa += 1; }
+			}
+			for (int col = 1; col <= m; col++) {  // (:4270-4331)
+				const int p = col - 1;
+				bool have = false;
+				if (lv(col, F_SM)) { fa += 1; have = true; }
+				if (lv(p, F_MM)) { fa += 1; if (have) fl += 1; have = true; }
+				if (lv(p, F_IM)) { fa += 1; if (have) fl += 1; have = true; }
+				if (lv(p, F_DM)) { fa += 1; if (have) fl += 1; have = true; }
+				fa += 1;
+				if (have) { fl += 1; fa += 2; }
+				have = false;
+				if (lv(col, F_SI)) { fa += 1; have = true; }
+				if (lv(col, F_II)) { fa += 1; if (have) fl += 1; have = true; }
+				if (lv(col, F_MI)) { fa += 1; if (have) fl += 1; have = true; }
+				fa += 1;
+				if (have) { fl += 1; fa += 2; }
+				bool dh = false;
+				if (lv(p, F_MD)) { fa += 1; dh = true; }
+				if (lv(p, F_DD)) { fa += 1; if (dh) fl += 1; }
+				if (lv(col, F_MSKIP)) { fl += 1; fa += 1; }
+				if (lv(col, F_ISKIP)) { fl += 1; fa += 1; }
+			}
+			if (g.skip_live) { fl += 1; fa += 1; }
+			hm.live_ls_bwd += bl; hm.live_add_bwd += ba; hm.live_ls_fwd += fl; hm.live_add_fwd += fa;
+		}
+	}
 	// labels, types
 	hm.label.assign(d->label, d->label + H);
 	hm.seg_type.assign((const uint8_t*)d->seg_type, (const uint8_t*)d->seg_type + S);
@@ -371,6 +466,17 @@ struct tdg_model {
 	size_t slot_bytes_full = 0, slot_bytes_bwd = 0;
 	int dyn_cols = 0;  // shared-memory profile state for the column-loop paths, when it fits beside the table and the model
 };
+
+extern "C" int tdg_desc_live_ops(const tdg_model_desc* desc, double out[4])
+{
+	if (!out) return fail(TDG_EINVAL, "NULL argument");
+	HostModel hm;
+	std::string err;
+	const int rc = derive_model(desc, hm, err);
+	if (rc != TDG_OK) return fail(rc, "%s", err.c_str());
+	out[0] = hm.live_ls_bwd; out[1] = hm.live_add_bwd; out[2] = hm.live_ls_fwd; out[3] = hm.live_add_fwd;
+	return TDG_OK;
+}
 
 extern "C" int tdg_model_validate(const tdg_model_desc* desc, char* errbuf, size_t errbuf_len)
 {
@@ -735,7 +841,7 @@ static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full, int
 	size_t free_b = 0, total_b = 0;
 	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return d.ctas; }
 	const double budget = 0.90 * (double)(free_b + d.scratch_bytes);
-	const double per_cta = (double)kBlock * (double)(full ? m->slot_bytes_full : m->slot_bytes_bwd);
+	const double per_cta = (double)num_lanes() * (double)kBlock * (double)(full ? m->slot_bytes_full : m->slot_bytes_bwd);
 	long fit = (long)(budget / per_cta);
 	if (const char* e = getenv("TDG_WAVE_CTAS")) { const long cap = atol(e); if (cap > 0) fit = std::min(fit, cap); }  // tests: force small waves
 	if (fit < 1) fit = 1;
@@ -744,12 +850,18 @@ static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full, int
 	return (int)std::min<long>(std::min<long>(d.ctas, fit), need);
 }
 
-static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool full, int wave_ctas)
+static size_t lane_scratch_bytes(const tdg_model* m, bool full, int wave_ctas)
+{
+	const size_t slots = (size_t)wave_ctas * kBlock;
+	return slots * (full ? m->slot_bytes_full : m->slot_bytes_bwd) + 10 * 256;
+}
+
+static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool full, int wave_ctas, int lane = 0)
 {
 	const HostModel& hm = m->hm;
 	const size_t slots = (size_t)wave_ctas * kBlock;
 	const size_t W = (size_t)m->max_len + 2;
-	char* p = (char*)d.scratch;
+	char* p = (char*)d.scratch + (size_t)lane * lane_scratch_bytes(m, full, wave_ctas);
 	auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) / 256 * 256; return q; };
 	a.sb = (float*)take(slots * hm.S * W * 4);
 	if (full) {
@@ -764,8 +876,7 @@ static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool
 
 static size_t scratch_need(const tdg_model* m, bool full, int wave_ctas)
 {
-	const size_t slots = (size_t)wave_ctas * kBlock;
-	return slots * (full ? m->slot_bytes_full : m->slot_bytes_bwd) + 10 * 256;
+	return (size_t)num_lanes() * lane_scratch_bytes(m, full, wave_ctas);
 }
 
 // Queue all waves of one shard on `stream`.  Returns kernel launches queued (<0 on error).
@@ -791,8 +902,23 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	a.want_labels = want_labels;
 	const int wave = wave_ctas * kBlock;
 	int launches = 0;
-	for (int w0 = 0; w0 < s.n; w0 += wave) {
+	const int lanes = num_lanes();
+	cudaStream_t const main_stream = stream;
+	if (lanes > 1) {
+		if (!d.lane2) {
+			if (cudaStreamCreateWithFlags(&d.lane2, cudaStreamNonBlocking) != cudaSuccess ||
+			    cudaEventCreateWithFlags(&d.lane_fork, cudaEventDisableTiming) != cudaSuccess ||
+			    cudaEventCreateWithFlags(&d.lane_join, cudaEventDisableTiming) != cudaSuccess) { fail(TDG_ECUDA, "lane stream creation failed"); return -1; }
+		}
+		cudaEventRecord(d.lane_fork, main_stream);
+		cudaStreamWaitEvent(d.lane2, d.lane_fork, 0);
+	}
+	for (int w0 = 0, wi = 0; w0 < s.n; w0 += wave, wi++) {
 		const int nw = std::min(wave, s.n - w0);
+		if (lanes > 1) {
+			stream = (wi % lanes) ? d.lane2 : main_stream;
+			carve_scratch(a, m, d, !bwd_only, wave_ctas, wi % lanes);
+		}
 		a.n_reads = nw;
 		a.seq = s.seq + (size_t)(w0 / 32) * b->words * 32;
 		a.len = s.len + w0;
@@ -820,6 +946,10 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 			}
 		}
 	}
+	if (lanes > 1) {
+		cudaEventRecord(d.lane_join, d.lane2);
+		cudaStreamWaitEvent(main_stream, d.lane_join, 0);
+	}
 	return launches;
 }
 
@@ -845,15 +975,14 @@ static int check_compat(tdg_model* m, tdg_batch* b, const tdg_run_params* p)
 {
 	if (!m || !b) return fail(TDG_EINVAL, "NULL model or batch");
 	if (m->ctx != b->ctx) return fail(TDG_EINVAL, "model and batch belong to different contexts");
-	int need = b->max_len;
+	// k_label clears / stages labels over the whole read even when only a -start/-end window is decoded,
+	// so the model must be sized for the longest read in either case
+	int need = 0;
+	for (int i = 0; i < b->n; i++) need = std::max(need, b->h_len[i]);
 	if (p && (p->matchstart != -1 || p->matchend != -1)) {
 		if (p->matchstart < 0 || p->matchend <= p->matchstart) return fail(TDG_EINVAL, "bad -start/-end window %d..%d", p->matchstart, p->matchend);
-		need = p->matchend - p->matchstart;
 		for (int i = 0; i < b->n; i++)
 			if (b->h_len[i] < p->matchend) return fail(TDG_EINVAL, "read %d (length %d) shorter than the -end window %d", i, b->h_len[i], p->matchend);
-	} else {
-		need = 0;
-		for (int i = 0; i < b->n; i++) need = std::max(need, b->h_len[i]);
 	}
 	if (need > m->max_len) return fail(TDG_EINVAL, "read length %d exceeds the model's max_len %d (rebuild the model, cf. barcode_hmm.c:292-310)", need, m->max_len);
 	return TDG_OK;
@@ -972,31 +1101,36 @@ extern "C" int tdg_arch_compare(tdg_context* ctx, tdg_model* const* models, int 
 		assign_shards(b);
 		const size_t nd = ctx->devs.size();
 		std::vector<float*> d_scores(nd, nullptr);
-		auto cleanup = [&] { for (size_t k = 0; k < nd; k++) if (d_scores[k]) { cudaSetDevice(ctx->devs[k].dev); cudaFree(d_scores[k]); } };
-		for (size_t k = 0; k < nd; k++) {
-			DeviceCtx& d = ctx->devs[k];
-			Shard& s = b->shard[k];
-			if (s.n == 0) continue;
-			CK(cudaSetDevice(d.dev));
-			if ((rc = devalloc(&d_scores[k], (size_t)num_arch * s.n))) { cleanup(); return rc; }
-			if ((rc = upload_shard(b, (int)k, s.copy))) { cleanup(); return rc; }
-			CK(cudaEventRecord(s.h2d_done, s.copy));
-			CK(cudaStreamWaitEvent(d.compute, s.h2d_done, 0));
-			for (int a = 0; a < num_arch; a++) {
-				const int wc = plan_wave_ctas(models[a], d, false, s.n);
-				if ((rc = ensure_scratch(d, scratch_need(models[a], false, wc)))) { cleanup(); return rc; }
-				if (queue_decode(ctx, models[a], TDG_MODE_ARCH_COMP, nullptr, b, (int)k, d.compute, d_scores[k] + (size_t)a * s.n, wc) < 0) { cleanup(); return TDG_ECUDA; }
+		auto body = [&]() -> int {  // every early return leaves through the cleanup below
+			for (size_t k = 0; k < nd; k++) {
+				DeviceCtx& d = ctx->devs[k];
+				Shard& s = b->shard[k];
+				if (s.n == 0) continue;
+				CK(cudaSetDevice(d.dev));
+				if ((rc = devalloc(&d_scores[k], (size_t)num_arch * s.n))) return rc;
+				if ((rc = upload_shard(b, (int)k, s.copy))) return rc;
+				CK(cudaEventRecord(s.h2d_done, s.copy));
+				CK(cudaStreamWaitEvent(d.compute, s.h2d_done, 0));
+				for (int a = 0; a < num_arch; a++) {
+					const int wc = plan_wave_ctas(models[a], d, false, s.n);
+					if ((rc = ensure_scratch(d, scratch_need(models[a], false, wc)))) return rc;
+					if (queue_decode(ctx, models[a], TDG_MODE_ARCH_COMP, nullptr, b, (int)k, d.compute, d_scores[k] + (size_t)a * s.n, wc) < 0) return TDG_ECUDA;
+				}
 			}
-		}
-		for (size_t k = 0; k < nd; k++) {
-			Shard& s = b->shard[k];
-			if (s.n == 0) continue;
-			CK(cudaSetDevice(ctx->devs[k].dev));
-			CK(cudaStreamSynchronize(ctx->devs[k].compute));
-			for (int a = 0; a < num_arch; a++)
-				CK(cudaMemcpy(all.data() + (size_t)a * n + s.first, d_scores[k] + (size_t)a * s.n, (size_t)s.n * 4, cudaMemcpyDeviceToHost));
-		}
-		cleanup();
+			for (size_t k = 0; k < nd; k++) {
+				Shard& s = b->shard[k];
+				if (s.n == 0) continue;
+				CK(cudaSetDevice(ctx->devs[k].dev));
+				CK(cudaStreamSynchronize(ctx->devs[k].compute));
+				for (int a = 0; a < num_arch; a++)
+					CK(cudaMemcpy(all.data() + (size_t)a * n + s.first, d_scores[k] + (size_t)a * s.n, (size_t)s.n * 4, cudaMemcpyDeviceToHost));
+			}
+			return TDG_OK;
+		};
+		rc = body();
+		for (size_t k = 0; k < nd; k++)
+			if (d_scores[k]) { cudaSetDevice(ctx->devs[k].dev); cudaStreamSynchronize(ctx->devs[k].compute); cudaFree(d_scores[k]); }
+		if (rc) return rc;
 	}
 	if (b_scores) memcpy(b_scores, all.data(), all.size() * 4);
 	// per-"thread" float sums in read order over the reference's static slices, added in thread order

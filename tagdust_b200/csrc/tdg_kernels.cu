@@ -84,6 +84,17 @@ __device__ __forceinline__ void st_keep(float* p, float v, uint64_t pol)
 #endif
 }
 
+// Mb/Ib scratch load of k_forward.  -DTDG_EXP_FWD_NOLOAD (experiment builds only, scripts/build_variant.sh) replaces it
+// with a constant: the kernel's compute-only time, i.e. what k_forward would cost if the backward values came for free.
+__device__ __forceinline__ float2 ld_bw(const float2* p)
+{
+#ifdef TDG_EXP_FWD_NOLOAD
+	return make_float2(-3.0f, -5.0f);
+#else
+	return __ldcs(p);
+#endif
+}
+
 typedef uint32_t TabAddr;  // shared-memory byte address of the table minus (0x4B000000 << 2)
 
 __device__ __forceinline__ TabAddr make_tab_addr(const float* tab)
@@ -419,7 +430,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 }
 
 template <bool STORE>
-__global__ void __launch_bounds__(kBlock, 1) k_backward(const KArgs a)
+__global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a)
 {
 	extern __shared__ float smem_f[];
 	const Smem sm = stage_smem(a, smem_f);
@@ -541,13 +552,13 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 		}
 		if (NC > 0) {
 #pragma unroll
-			for (int g = 0; g < NB; ++g) bn[g] = __ldcs(&bwq[(size_t)g * kBlock]);
+			for (int g = 0; g < NB; ++g) bn[g] = ld_bw(&bwq[(size_t)g * kBlock]);
 		}
 		const float sM0 = STD ? rec[F_SM] : 0.0f;
 		// column-loop path: Mb/Ib are fetched one stored column ahead of their use (column 0 of the next position
 		// while the last column of this one is computed), so the loads overlap the logsums instead of preceding them
 		float2 b_ahead = make_float2(NEG_INF, NEG_INF);
-		if (NC == 0) b_ahead = __ldcs(&bwq[0]);
+		if (NC == 0) b_ahead = ld_bw(&bwq[0]);
 		float TP = NEG_INF;
 		int pfirst = 0xFFFF, plast = 0;  // positions whose posterior is >= -104 (exp != 0), for k_label
 		float ps1 = first_seg ? 0.0f : ps_arr[0];  // psilent[0]
@@ -575,7 +586,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 			if (NC > 0) {
 				if (i < a.lmax) bwq += bstep;  // position i+1, clamped to the scratch
 #pragma unroll
-				for (int g = 0; g < NB; ++g) { bc[g] = bn[g]; bn[g] = __ldcs(&bwq[(size_t)g * kBlock]); }
+				for (int g = 0; g < NB; ++g) { bc[g] = bn[g]; bn[g] = ld_bw(&bwq[(size_t)g * kBlock]); }
 			}
 			cs_n = ld_keep(csp + kBlock, keep);
 			if (!first_seg) ps_n = ld_keep(psp + kBlock, keep);
@@ -588,7 +599,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 					const float* r = rec;
 					const uint32_t lv = STD ? 0u : __float_as_uint(r[F_LIVE]);
 					const float2 b = NC > 0 ? bc[0] : b_ahead;
-					if (NC == 0 && ncs > 1) b_ahead = __ldcs(&bwq[((size_t)(i - 1) * ncs + 1) * kBlock]);
+					if (NC == 0 && ncs > 1) b_ahead = ld_bw(&bwq[((size_t)(i - 1) * ncs + 1) * kBlock]);
 					const float eM = em[x], eI = STD ? eIu : em[5 + x];
 					const bool lsm = live_of<STD>(nc, 0, F_SM, lv);
 					const bool lsi = live_of<STD>(nc, 0, F_SI, lv);
@@ -624,8 +635,8 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 						else b = NC > 0 ? bc[(NC > 0 && !(STD && g == NC - 1)) ? g : 0] : b_ahead;
 						if (NC == 0) {
 							// next stored column of this position, or column 0 of the next position (clamped to the scratch)
-							if (g + 1 < ncs) b_ahead = __ldcs(&bwq[((size_t)(i - 1) * ncs + g + 1) * kBlock]);
-							else if (g + 1 == nc && i < a.lmax) b_ahead = __ldcs(&bwq[((size_t)i * ncs) * kBlock]);
+							if (g + 1 < ncs) b_ahead = ld_bw(&bwq[((size_t)(i - 1) * ncs + g + 1) * kBlock]);
+							else if (g + 1 == nc && i < a.lmax) b_ahead = ld_bw(&bwq[((size_t)i * ncs) * kBlock]);
 						}
 						const float eM = em[g * kEmitRec + x], eI = STD ? eIu : em[g * kEmitRec + 5 + x];
 						const float oldMg = M[g], oldIg = I[g];
@@ -683,7 +694,7 @@ __device__ __forceinline__ float s2p_f(float p)
 	return (float)exp((double)p);
 }
 
-__global__ void __launch_bounds__(kBlock, 1) k_forward(const KArgs a)
+__global__ void __launch_bounds__(kBlock, 512 / kBlock) k_forward(const KArgs a)
 {
 	extern __shared__ float smem_f[];
 	const Smem sm = stage_smem(a, smem_f);

@@ -199,7 +199,10 @@ extern "C" int tdg_fastq_open(const char* path, int fasta, tdg_fastq** out)
 	if (gz || bz) {
 		const char* tool = bz ? "bzcat" : "zcat";
 		if (gz && (access("/usr/bin/gzcat", X_OK) == 0 || access("/bin/gzcat", X_OK) == 0)) tool = "gzcat";
-		std::string cmd = std::string(tool) + " '" + p + "'";
+		// the path goes to sh -c inside single quotes: a quote in it is written as '\'' (close, escaped quote, reopen)
+		std::string quoted;
+		for (char ch : p) { if (ch == '\'') quoted += "'\\''"; else quoted += ch; }
+		std::string cmd = std::string(tool) + " '" + quoted + "'";
 		f->pipe = popen(cmd.c_str(), "r");
 		if (!f->pipe) { delete f; return failf(TDG_EIO, "cannot run: %s", cmd.c_str()); }
 	} else {
