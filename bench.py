@@ -102,8 +102,8 @@ def ncu_traffic(kernel):
     return (k["dram_bytes_read"] + k["dram_bytes_write"] if k else None), d.get("source"), (k or {})
 
 
-def write_fastq_fixed(path, codes, read_len):
-    """Fixed-width FASTQ records (name, 150 nt, '+', qualities) written with numpy, no Python loop."""
+def fastq_block(codes, read_len):
+    """Fixed-width FASTQ records (name, 150 nt, '+', qualities) as one uint8 matrix, built with numpy (no Python loop)."""
     n = codes.shape[0]
     name_w = 11
     rec = np.empty((n, 1 + name_w + 1 + read_len + 3 + read_len + 1), np.uint8)
@@ -118,31 +118,113 @@ def write_fastq_fixed(path, codes, read_len):
     rec[:, o:o + 3] = np.frombuffer(b"\n+\n", np.uint8); o += 3
     rec[:, o:o + read_len] = ord("I"); o += read_len
     rec[:, o] = ord("\n")
-    rec.tofile(path)
+    return rec
 
 
-def files_e2e(ctx, model, tags, codes, n_reads, threads):
-    """FASTQ file -> tdg_demux_run (reader, pack, GPU, extraction, demultiplexed FASTQ files), the
-    streaming layer of SURVEY 8(f) rank 1.  Returns reads/s and the stage times."""
+def write_fastq_fixed(path, codes, read_len, repeats=1):
+    rec = fastq_block(codes, read_len)
+    with open(path, "wb") as fh:
+        for _ in range(repeats):
+            rec.tofile(fh)
+
+
+def files_e2e(ctx, model, tags, codes, n_reads, threads, n_dev, expect_extracted_per_block=None):
+    """FASTQ file -> tdg_demux_run (reader, pack, GPU, extraction, demultiplexed FASTQ files), the streaming layer of
+    SURVEY 8(f) rank 1, on ONE context over `n_dev` devices: a fixed job, so the N = 1, 2, 4, 8 values form a
+    strong-scaling curve.  The file is a block of synthetic cfg2 reads written `repeats` times into /dev/shm."""
     import shutil
     import tempfile
     from tagdust_b200 import stream
-    tmp = tempfile.mkdtemp(prefix="tdg_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix="tdg_bench_", dir=shm)
     try:
+        block = min(codes.shape[0], n_reads)
+        rec_bytes = 1 + 11 + 1 + READ_LEN + 3 + READ_LEN + 1
+        repeats = max(1, -(-n_reads // block))
+        free = shutil.disk_usage(tmp).free
+        while repeats > 1 and 2.2 * repeats * block * rec_bytes > 0.8 * free:   # input + output must fit
+            repeats -= 1
+        total = block * repeats
         fq = os.path.join(tmp, "in.fq")
-        write_fastq_fixed(fq, codes[:n_reads], READ_LEN)
+        t0 = time.perf_counter()
+        write_fastq_fixed(fq, codes[:block], READ_LEN, repeats)
+        log(f"[files] wrote {total} reads ({os.path.getsize(fq) / 1e9:.2f} GB) in {time.perf_counter() - t0:.1f}s")
         t0 = time.perf_counter()
         st = stream.demux_run(ctx, [dict(path=fq, model=model, num_read_segments=1, threshold=THRESHOLD, max_seq_len=READ_LEN)],
                               os.path.join(tmp, "out"), barcode_input=0, barcode_names=list(tags), minlen=16, dust=100, threads=threads)
         dt = time.perf_counter() - t0
         out_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.startswith("out"))
-        return {"value": n_reads / dt, "unit": "reads/s", "reads": n_reads, "seconds": dt, "host_threads": threads,
-                "input_bytes": os.path.getsize(fq), "output_bytes": out_bytes,
-                "stage_busy_s": {k: st[k] for k in ("seconds_split", "seconds_parse", "seconds_gpu_wait", "seconds_write")},
-                "extracted": st["num_EXTRACT_SUCCESS"],
-                "what": "tdg_demux_run: FASTQ file in /dev/shm -> 49 demultiplexed FASTQ files, byte-identical format to print_all"}
+        out = {"value": total / dt, "unit": "reads/s", "reads": total, "seconds": dt, "host_threads": threads, "n_devices": n_dev,
+               "scaling": "strong (fixed job, one tdg_context over n_devices)",
+               "input_bytes": os.path.getsize(fq), "output_bytes": out_bytes,
+               "stage_busy_s": {k: st[k] for k in ("seconds_split", "seconds_parse", "seconds_gpu_wait", "seconds_write")},
+               "extracted": st["num_EXTRACT_SUCCESS"], "total_read": st["total_read"],
+               "what": "tdg_demux_run: FASTQ file in /dev/shm -> 49 demultiplexed FASTQ files, byte-identical format to print_all; "
+                       "the GPU returns R-run spans, label rows stay on the device"}
+        if expect_extracted_per_block is not None:
+            out["extracted_matches_kernel_run"] = bool(st["num_EXTRACT_SUCCESS"] == expect_extracted_per_block * repeats
+                                                       and st["total_read"] == total)
+        return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def one_context_e2e(ctxN, modelN, codes, lens, kw, steps, n_dev):
+    """The C-ABI call with host arrays (pack -> H2D -> kernels -> D2H, double buffered) on ONE context that shards every
+    batch over all devices (tdg_plan_shards), driven by one host thread: the library's own multi-device path."""
+    from tagdust_b200.api import MODE_GET_LABEL
+    reps = max(1, min(n_dev, 4))            # a larger batch per step so that every device gets several waves
+    big_codes = np.concatenate([codes] * reps) if reps > 1 else codes
+    big_lens = np.concatenate([lens] * reps) if reps > 1 else lens
+    n = big_codes.shape[0]
+    os.environ["TDG_PACK_THREADS"] = str(max(4, host_threads() // 2))
+    bs = [ctxN.batch(n, READ_LEN) for _ in range(2)]
+
+    def run(k):
+        pending = None
+        for s in range(k):
+            b = bs[s % 2]
+            b.clear()
+            b.append(big_codes, big_lens)
+            ctxN.submit(modelN, b, MODE_GET_LABEL, **kw)
+            if pending is not None:
+                ctxN.wait(pending, copy=False)
+            pending = b
+        ctxN.wait(pending, copy=False)
+
+    run(2)
+    t0 = time.perf_counter()
+    run(steps)
+    dt = time.perf_counter() - t0
+    for b in bs:
+        b.close()
+    os.environ.pop("TDG_PACK_THREADS", None)
+    return {"value": n * steps / dt, "unit": "reads/s", "n_devices": n_dev, "reads_per_step": int(n), "steps": steps,
+            "pack_threads": max(4, host_threads() // 2),
+            "what": "tdg_batch_append_codes + tdg_submit + tdg_wait on one tdg_context over all devices, one host thread, host arrays"}
+
+
+def multi_device_check(ctx1, model1, ctxN, modelN, codes, lens, kw, n):
+    """The same reads through a one-device context and through one context sharded over all devices
+    (tdg_plan_shards: contiguous, tile-aligned shards; output order = input order): every output must have the same bits."""
+    from tagdust_b200.api import MODE_GET_LABEL
+    n = min(n, codes.shape[0])
+    out = []
+    for ctx, model in ((ctx1, model1), (ctxN, modelN)):
+        b = ctx.batch(n, READ_LEN)
+        b.append(codes[:n], lens[:n])
+        out.append(ctx.run_phmm(model, b, MODE_GET_LABEL, want_spans=True, **kw))
+        b.close()
+    a, c = out
+    bad = np.zeros(n, bool)
+    for k in ("b_score", "f_score", "r_score", "bar_prob", "mapq"):
+        bad |= a[k].view(np.uint32) != c[k].view(np.uint32)
+    for k in ("read_type", "barcode", "fingerprint", "extracted"):
+        bad |= a[k] != c[k]
+    bad |= (a["labels"] != c["labels"]).any(axis=1)
+    bad |= (a["spans"] != c["spans"]).reshape(n, -1).any(axis=1)
+    return {"reads": int(n), "devices": ctxN.device_count, "mismatches": int(bad.sum()),
+            "what": "one tdg_context over all devices vs a one-device context, all outputs compared bit for bit"}
 
 
 def peaks():
@@ -377,11 +459,27 @@ def run_gpu_arm(args):
                             "frac": hbm_achieved / pk.get("hbm_gbs") if pk.get("hbm_gbs") else None, "traffic": traffic,
                             "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk_src,
                             "note": "k_backward writes and k_forward reads this stream once; ncu traffic adds the silent-state arrays"}
-    if rank == 0 and world == 1 and not args.no_files:
+    # ---- strong scaling, file to files: rank 0 alone drives ONE context over all N devices (the other ranks have
+    #      released their device memory and wait at the barrier below)
+    for b in batches:
+        b.close()
+    batches = []
+    if rank != 0:
+        model.close(); ctx.close()
+    barrier()
+    if rank == 0 and not args.no_files:
         try:
-            line["e2e_files"] = files_e2e(ctx, model, tags, codes, min(n_reads, args.files_reads), host_threads())
+            ctxN = ctx if world == 1 else Context(n_devices=world)
+            modelN = model if world == 1 else ctxN.model(desc, READ_LEN)
+            if world > 1:
+                line["multi_device_check"] = multi_device_check(ctx, model, ctxN, modelN, codes, lens, kw, 2 * 148 * 512 * world + 1000)
+                line["e2e_one_context"] = one_context_e2e(ctxN, modelN, codes, lens, kw, args.steps, world)
+            extracted_block = int((res["read_type"][:min(n_reads, args.files_reads)] == 0).sum())
+            line["e2e_files"] = files_e2e(ctxN, modelN, tags, codes, args.files_reads, host_threads(), world, extracted_block)
+            if world > 1:
+                modelN.close(); ctxN.close()
         except Exception as exc:  # the streaming layer is an extra line, never a reason to lose the bench
-            line["e2e_files"] = {"error": str(exc)}
+            line["e2e_files"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         n_cpu = max(threads * 2500, 20000)   # ~10 s of host work
@@ -391,10 +489,9 @@ def run_gpu_arm(args):
                                 "sample": f"{n_cpu} reads of the same workload, run_pHMM(MODE_GET_LABEL), {threads} pthreads, {times[0]:.1f} s"}
     if rank == 0:
         emit(line)
-    for b in batches:
-        b.close()
-    model.close()
-    ctx.close()
+        model.close()
+        ctx.close()
+    barrier()
     dist_util.finalize()
 
 
@@ -424,7 +521,7 @@ def main():
     ap.add_argument("--reads", type=int, default=32 * 148 * 512, help="reads per step per GPU (default 32 waves)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the FASTQ-file -> demultiplexed-files measurement")
-    ap.add_argument("--files-reads", type=int, default=4_000_000)
+    ap.add_argument("--files-reads", type=int, default=16_000_000, help="reads of the file-to-files job (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

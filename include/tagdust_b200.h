@@ -87,7 +87,11 @@ typedef struct tdg_run_params {
 	int32_t matchstart;           /* param->matchstart, -1 = unset */
 	int32_t matchend;             /* param->matchend,   -1 = unset */
 	int32_t dust;                 /* param->dust; 0 = off (dust_sequences :2407) */
-	int32_t want_labels;          /* 0: skip the label DP/traceback in MODE_GET_PROB */
+	int32_t want_labels;          /* 1: ri->labels rows are returned (tdg_result.labels).  0: MODE_GET_PROB skips the label
+	                                 DP/traceback altogether; MODE_GET_LABEL still runs it (extraction needs it) but keeps the
+	                                 rows on the device -- most of the device->host bytes of a read */
+	int32_t want_spans;           /* 1 (MODE_GET_LABEL): return the R-labelled runs of every extracted read (tdg_result.spans),
+	                                 i.e. what make_extracted_read (barcode_hmm.c:3325-3356) leaves of it */
 } tdg_run_params;
 
 /* Per-read results (host arrays owned by the batch; valid after tdg_wait/tdg_run). */
@@ -104,7 +108,11 @@ typedef struct tdg_result {
 	                                 even if dust later overwrote read_type */
 	const int32_t* barcode;       /* ri->barcode   (-1 if not set) */
 	const int32_t* fingerprint;   /* ri->fingerprint (-1 if not set) */
-	const uint8_t* labels;        /* ri->labels[0..len] at labels + r*label_stride */
+	const uint8_t* labels;        /* ri->labels[0..len] at labels + r*label_stride; NULL unless want_labels */
+	int32_t        span_stride;   /* (start, len) pairs per read in `spans` = R segments of the architecture + 1 */
+	const uint16_t* spans;        /* want_spans: spans[(r*span_stride + k)*2] = first residue (0-based), [.. + 1] = length of the
+	                                 k-th run of residues whose label lies in an R segment; len 0 ends the list.  Only filled for
+	                                 reads with extracted == 1; NULL unless want_spans */
 } tdg_result;
 
 /* ---- lifetime ------------------------------------------------------------------- */

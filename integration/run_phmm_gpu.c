@@ -310,7 +310,7 @@ static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_
 		if (numseq <= 0) return kslOK;
 		tdg_run_params rq;
 		rq.confidence_threshold = param->confidence_threshold; rq.minlen = param->minlen;
-		rq.matchstart = param->matchstart; rq.matchend = param->matchend; rq.dust = 0; rq.want_labels = 0;
+		rq.matchstart = param->matchstart; rq.matchend = param->matchend; rq.dust = 0; rq.want_labels = 0; rq.want_spans = 0;
 		if (ensure_batch(param, numseq < CH ? numseq : CH, order[numseq - 1]->len > 1 ? order[numseq - 1]->len : 1) != kslOK) rc = kslFAIL;
 		for (c0 = 0; c0 < numseq && rc == kslOK; c0 += CH) {
 			const int n = numseq - c0 < CH ? numseq - c0 : CH;
@@ -343,6 +343,7 @@ static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_
 	 * keep dust on the host then, after the artifact filter */
 	rp.dust = reference_fasta ? 0 : param->dust;
 	rp.want_labels = (mode == MODE_GET_LABEL);
+	rp.want_spans = 0;
 	tdg_result res;
 	if (tdg_run(g_ctx, m, mode == MODE_GET_LABEL ? TDG_MODE_GET_LABEL : TDG_MODE_GET_PROB, &rp, g_batch, &res) != TDG_OK)
 	{

@@ -404,6 +404,116 @@ static int dust_low_complexity(const uint8_t* seq, int rlen, int dust_cut)
 	return s > dust_cut;
 }
 
+/* ---- -ref artifact filter --------------------------------------------------------------------------
+ * match_to_reference (barcode_hmm.c:2478-2583) with the two Myers bit-vector variants it calls:
+ * groups of four reads of a thread slice -> validate_bpm_sse -> bmp_single (misc.c:718-765), best match over all
+ * reference sequences, forward strand first; the last (slice length mod 4) reads of a slice -> bpm_check_error
+ * (misc.c:572-636), first reference sequence within the error cut-off.  The pattern is the read as
+ * make_extracted_read left it (spacer 65 outside R segments). */
+static const uint8_t* g_ref_string = 0; static const int32_t* g_ref_index = 0; static int g_ref_numseq = 0, g_ref_cut = 2;
+void orc_set_reference(const uint8_t* string, const int32_t* s_index, int numseq, int filter_error)
+{
+	g_ref_string = string; g_ref_index = s_index; g_ref_numseq = numseq; g_ref_cut = filter_error;
+}
+
+/* misc.c:718-765: semi-global edit distance of the first min(m, 63) pattern characters against the target */
+int orc_bmp_single(const uint8_t* t, const uint8_t* p, int n, int m)
+{
+	uint64_t B[4] = {0, 0, 0, 0}, VP, VN = 0, D0, HN, HP, X, MASK;
+	int64_t diff; int k, i;
+	if (m > 63) m = 63;
+	diff = m; k = m;
+	for (i = 0; i < m; i++) if (p[i] != 65) B[p[i] & 3u] |= (uint64_t)1 << i;
+	VP = ((uint64_t)1 << m) - 1;
+	MASK = (uint64_t)1 << (m - 1);
+	for (i = 0; i < n; i++) {
+		X = B[t[i] & 3u] | VN;
+		D0 = ((VP + (X & VP)) ^ VP) | X;
+		HN = VP & D0;
+		HP = VN | ~(VP | D0);
+		X = HP << 1;
+		VN = X & D0;
+		VP = (HN << 1) | ~(X | D0);
+		if (HP & MASK) diff++;
+		if (HN & MASK) diff--;
+		if (diff < k) k = (int)diff;
+	}
+	return k;
+}
+
+/* misc.c:572-636.  The reference shifts 1 by the character index and by (new_len - 1) without range checks; on x86-64
+ * the shift count is taken modulo 64, which is what the compiled reference does and what is restated here. */
+int orc_bpm_check_error(const uint8_t* t, const uint8_t* p, int n, int m)
+{
+	uint64_t B[4] = {0, 0, 0, 0}, VP = ~(uint64_t)0, VN = 0, D0, HN, HP, X, MASK, diff = (uint64_t)m, k;
+	int i, new_len = 0, sh;
+	for (i = 0; i < m; i++) if (p[i] != 65) { B[p[i] & 3] |= (uint64_t)1 << (i & 63); new_len++; }
+	if (new_len > 31) new_len = 31;
+	k = (uint64_t)new_len;
+	sh = (new_len - 1) & 63;
+	MASK = (uint64_t)1 << sh;
+	for (i = 0; i < n; i++) {
+		X = B[t[i] & 3] | VN;
+		D0 = ((VP + (X & VP)) ^ VP) | X;
+		HN = VP & D0;
+		HP = VN | ~(VP | D0);
+		X = HP << 1;
+		VN = X & D0;
+		VP = (HN << 1) | ~(X | D0);
+		diff += (HP & MASK) >> sh;
+		diff -= (HN & MASK) >> sh;
+		if (diff < k) k = diff;
+	}
+	return (int)k;
+}
+
+/* reverse_complement (misc.c:829-848): spacers stay, A<->T, C<->G, N stays (nuc_code.c:68-72) */
+static void revcomp(const uint8_t* p, int len, uint8_t* out)
+{
+	static const uint8_t rc[5] = {3, 2, 1, 0, 4};
+	int i, c = 0;
+	for (i = len - 1; i >= 0; i--) out[c++] = (p[i] == 65) ? 65 : rc[p[i] < 5 ? p[i] : 4];
+	out[c] = 0;
+}
+
+/* one slice [start, end) of a run_pHMM / run_rna_dust call; seqs[i] = rewritten read i, 0-terminated */
+static void match_slice(uint8_t** seqs, const int32_t* lens, int32_t* read_type, int start, int end)
+{
+	int i, j, c;
+	int maxlen = 1;
+	uint8_t* rev;
+	for (i = start; i < end; i++) if (lens[i] > maxlen) maxlen = lens[i];
+	rev = malloc(maxlen + 2);
+	for (i = start; i <= end - 4; i += 4) {
+		for (c = 0; c < 4; c++) {
+			const int r = i + c;
+			int best = 100000, id = 0;
+			revcomp(seqs[r], lens[r], rev);
+			for (j = 0; j < g_ref_numseq; j++) {
+				const uint8_t* t = g_ref_string + g_ref_index[j];
+				const int n = g_ref_index[j + 1] - g_ref_index[j];
+				int e = lens[r] > 0 ? orc_bmp_single(t, seqs[r], n, lens[r]) : n;
+				if (e < best) { best = e; id = j + 1; }
+				e = lens[r] > 0 ? orc_bmp_single(t, rev, n, lens[r]) : n;
+				if (e < best) { best = e; id = j + 1; }
+			}
+			if (best <= g_ref_cut && read_type[r] == TDG_EXTRACT_SUCCESS) read_type[r] = (id << 8) | TDG_EXTRACT_FAIL_MATCHES_ARTIFACTS;
+		}
+	}
+	for (; i < end; i++) {
+		int hit = 0;
+		revcomp(seqs[i], lens[i], rev);
+		for (j = 0; j < g_ref_numseq && !hit; j++) {
+			const uint8_t* t = g_ref_string + g_ref_index[j];
+			const int n = g_ref_index[j + 1] - g_ref_index[j];
+			if (orc_bpm_check_error(t, seqs[i], n, lens[i]) <= g_ref_cut) hit = j + 1;
+			else if (orc_bpm_check_error(t, rev, n, lens[i]) <= g_ref_cut) hit = j + 1;
+		}
+		if (hit && read_type[i] == TDG_EXTRACT_SUCCESS) read_type[i] = (hit << 8) | TDG_EXTRACT_FAIL_MATCHES_ARTIFACTS;
+	}
+	free(rev);
+}
+
 int orc_decode_read(const tdg_model_desc* d, const uint8_t* seq, int len, int want_labels,
                     orc_read_out* out, uint8_t* labels)
 {
@@ -435,6 +545,7 @@ typedef struct orc_job {
 	float *mapq, *bar_prob, *f_score, *b_score, *r_score;
 	int32_t *read_type, *barcode, *fingerprint; uint8_t* labels; uint8_t* seq_out; int32_t* len_out;
 	float* b_scores; int n;
+	uint8_t** rw_seq; int32_t* rw_len;   /* -ref: the rewritten reads of the whole call */
 } orc_job;
 
 /* do_label_thread :2269 / do_probability_estimation :2174 */
@@ -463,7 +574,11 @@ static void* label_worker(void* arg)
 		seq[rlen + 1] = 0;
 		if (jb->mode == TDG_MODE_GET_LABEL) {
 			extract(d, p, lab, seq, &rlen, o.mapq, &o);
-			if (p->dust && dust_low_complexity(seq, rlen, p->dust)) o.read_type = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
+			if (g_ref_numseq) {  /* do_label_thread :2345-2354: extract all, then match_to_reference, then dust */
+				jb->rw_seq[i] = malloc(rlen + 2);
+				memcpy(jb->rw_seq[i], seq, rlen + 1); jb->rw_seq[i][rlen + 1] = 0;
+				jb->rw_len[i] = rlen;
+			} else if (p->dust && dust_low_complexity(seq, rlen, p->dust)) o.read_type = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
 		}
 		if (jb->mapq) jb->mapq[i] = o.mapq;
 		if (jb->bar_prob) jb->bar_prob[i] = o.bar_prob;
@@ -476,6 +591,13 @@ static void* label_worker(void* arg)
 		if (jb->labels) for (j = 0; j <= jb->len[i]; j++) jb->labels[(size_t)i * jb->stride + j] = lab[j];
 		if (jb->seq_out) for (j = 0; j < jb->len[i]; j++) jb->seq_out[(size_t)i * jb->stride + j] = seq[j];
 		if (jb->len_out) jb->len_out[i] = rlen;
+	}
+	if (jb->mode == TDG_MODE_GET_LABEL && g_ref_numseq && jb->read_type) {
+		match_slice(jb->rw_seq, jb->rw_len, jb->read_type, jb->start, jb->end);
+		for (i = jb->start; i < jb->end; i++) {
+			if (p->dust && dust_low_complexity(jb->rw_seq[i], jb->rw_len[i], p->dust)) jb->read_type[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
+			free(jb->rw_seq[i]);
+		}
 	}
 	free(lab); free(seq); work_free(w);
 	return NULL;
@@ -492,12 +614,14 @@ int orc_run(const tdg_model_desc* d, const tdg_run_params* p, int mode, int n,
 {
 	int t, interval, ml = max_len(n, len);
 	pthread_t* th; orc_job* jobs;
+	uint8_t** rw_seq = calloc(n > 0 ? n : 1, sizeof(uint8_t*)); int32_t* rw_len = calloc(n > 0 ? n : 1, sizeof(int32_t));
 	if (num_threads < 1) num_threads = 1;
 	orc_init_logsum();
 	th = calloc(num_threads, sizeof(pthread_t)); jobs = calloc(num_threads, sizeof(orc_job));
 	interval = (int)((double)n / (double)num_threads);
 	for (t = 0; t < num_threads; t++) {
 		orc_job* jb = &jobs[t];
+		jb->rw_seq = rw_seq; jb->rw_len = rw_len;
 		jb->d = d; jb->p = p; jb->mode = mode; jb->start = t * interval; jb->end = t * interval + interval;
 		jb->maxlen = ml; jb->codes = codes; jb->stride = stride; jb->len = len;
 		jb->mapq = mapq; jb->bar_prob = bar_prob; jb->f_score = f_score; jb->b_score = b_score; jb->r_score = r_score;
@@ -507,7 +631,25 @@ int orc_run(const tdg_model_desc* d, const tdg_run_params* p, int mode, int n,
 	jobs[num_threads - 1].end = n;
 	for (t = 0; t < num_threads; t++) pthread_create(&th[t], NULL, label_worker, &jobs[t]);
 	for (t = 0; t < num_threads; t++) pthread_join(th[t], NULL);
-	free(th); free(jobs);
+	free(th); free(jobs); free(rw_seq); free(rw_len);
+	return 0;
+}
+
+/* run_rna_dust :2043 + do_rna_dust :2370: every read SUCCESS, then match_to_reference, then dust, per static slice */
+int orc_run_rna_dust(int n, const uint8_t* codes, size_t stride, const int32_t* len, int num_threads, int dust, int32_t* read_type)
+{
+	int t, i, interval;
+	uint8_t** seqs = calloc(n > 0 ? n : 1, sizeof(uint8_t*));
+	if (num_threads < 1) num_threads = 1;
+	for (i = 0; i < n; i++) { seqs[i] = (uint8_t*)codes + (size_t)i * stride; read_type[i] = TDG_EXTRACT_SUCCESS; }
+	interval = (int)((double)n / (double)num_threads);
+	for (t = 0; t < num_threads; t++) {
+		const int start = t * interval, end = (t == num_threads - 1) ? n : t * interval + interval;
+		if (g_ref_numseq) match_slice(seqs, len, read_type, start, end);
+		for (i = start; i < end; i++)
+			if (dust && dust_low_complexity(seqs[i], len[i], dust)) read_type[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
+	}
+	free(seqs);
 	return 0;
 }
 

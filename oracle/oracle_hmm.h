@@ -33,6 +33,13 @@ int orc_run(const tdg_model_desc* d, const tdg_run_params* p, int mode, int n,
             int32_t* read_type, int32_t* barcode, int32_t* fingerprint, uint8_t* labels,
             uint8_t* seq_out, int32_t* len_out);
 
+/* -ref artifact filter (match_to_reference, barcode_hmm.c:2478-2583): installs the reference set (flat nuc codes +
+ * s_index[numseq+1]) used by the following orc_run(MODE_GET_LABEL) / orc_run_rna_dust calls; numseq 0 removes it */
+void orc_set_reference(const uint8_t* string, const int32_t* s_index, int numseq, int filter_error);
+int  orc_bmp_single(const uint8_t* t, const uint8_t* p, int n, int m);       /* misc.c:718-765 */
+int  orc_bpm_check_error(const uint8_t* t, const uint8_t* p, int n, int m);  /* misc.c:572-636 */
+int  orc_run_rna_dust(int n, const uint8_t* codes, size_t stride, const int32_t* len, int num_threads, int dust, int32_t* read_type);
+
 int orc_arch_compare(const tdg_model_desc* const* archs, int num_arch, int n,
                      const uint8_t* codes, size_t stride, const int32_t* len, int num_threads,
                      float* b_scores, float* arch_posterior);

@@ -333,6 +333,69 @@ int refh_run_phmm(struct model_bag* mb, struct parameters* param, int mode,
 	return status;
 }
 
+/* ---------------- -ref artifact filter (match_to_reference, barcode_hmm.c:2478-2583) ----------------
+ * A struct fasta built from flat arrays (string = nuc codes of all sequences back to back, s_index[numseq+1]);
+ * refh_set_reference(param, ...) installs it for the next refh_run_phmm / refh_run_rna_dust calls, numseq 0 removes it. */
+static struct fasta* refh_fasta = 0;
+static char refh_fasta_name[] = "refh.fa";
+
+void refh_set_reference(struct parameters* param, const unsigned char* string, const int* s_index, int numseq, int filter_error)
+{
+	int i;
+	if(refh_fasta){
+		free(refh_fasta->string); free(refh_fasta->s_index); free(refh_fasta->mer_hash); free(refh_fasta);
+		refh_fasta = 0;
+	}
+	param->reference_fasta = 0;
+	if(numseq <= 0) return;
+	refh_fasta = calloc(1, sizeof(struct fasta));
+	refh_fasta->numseq = numseq;
+	refh_fasta->string_len = s_index[numseq];
+	refh_fasta->string = malloc(s_index[numseq] + 8);
+	memcpy(refh_fasta->string, string, s_index[numseq]);
+	refh_fasta->s_index = malloc(sizeof(int) * (numseq + 1));
+	for(i = 0; i <= numseq; i++) refh_fasta->s_index[i] = s_index[i];
+	refh_fasta->mer_hash = calloc(numseq, sizeof(int));
+	param->reference_fasta = refh_fasta_name;
+	param->filter_error = filter_error;
+}
+
+/* run_pHMM(MODE_GET_LABEL) with the installed reference: read_type comes back as (sequence_id << 8) | 5 for artifacts */
+int refh_run_phmm_ref(struct model_bag* mb, struct parameters* param, int n, const unsigned char* codes, int stride,
+                      const int* lens, float* mapq, int* read_type, int* barcode, int* fingerprint, unsigned char* seq_out)
+{
+	struct read_info** ri = refh_make_reads(n, codes, stride, lens);
+	int i, j, status;
+	status = run_pHMM(0, mb, ri, param, refh_fasta, n, MODE_GET_LABEL);
+	for(i = 0; i < n; i++){
+		mapq[i] = ri[i]->mapq; read_type[i] = ri[i]->read_type; barcode[i] = ri[i]->barcode; fingerprint[i] = ri[i]->fingerprint;
+		if(seq_out) for(j = 0; j < lens[i]; j++) seq_out[(size_t)i*stride + j] = (unsigned char)ri[i]->seq[j];
+	}
+	free_read_info(ri, n);
+	return status;
+}
+
+/* run_rna_dust() (barcode_hmm.c:2043, :2370): files whose architecture is a single R segment */
+int refh_run_rna_dust(struct parameters* param, int n, const unsigned char* codes, int stride, const int* lens, int* read_type)
+{
+	struct read_info** ri = refh_make_reads(n, codes, stride, lens);
+	int i, status;
+	status = run_rna_dust(ri, param, refh_fasta, n);
+	for(i = 0; i < n; i++) read_type[i] = ri[i]->read_type;
+	free_read_info(ri, n);
+	return status;
+}
+
+/* the two Myers variants on their own (misc.c:572-636 bpm_check_error; :718-796 validate_bpm_sse -> bmp_single) */
+int refh_bpm_check_error(const unsigned char* t, const unsigned char* p, int n, int m){ return bpm_check_error(t, p, n, m); }
+int refh_bmp_single(const unsigned char* t, const unsigned char* p, int n, int m)
+{
+	unsigned char* q[4]; int l[4];
+	q[0] = q[1] = q[2] = q[3] = (unsigned char*)p; l[0] = l[1] = l[2] = l[3] = m;
+	validate_bpm_sse(q, l, (unsigned char*)t, n, 4);
+	return l[0];
+}
+
 /* run_pHMM() in MODE_ARCH_COMP over A models; returns the normalised
  * log-posteriors exactly as test_architectures.c:184 receives them.        */
 int refh_run_arch_comp(struct model_bag** archs, int num_arch, struct parameters* param,

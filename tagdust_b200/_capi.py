@@ -59,6 +59,7 @@ class RunParamsC(C.Structure):
         ("matchend", C.c_int32),
         ("dust", C.c_int32),
         ("want_labels", C.c_int32),
+        ("want_spans", C.c_int32),
     ]
 
 
@@ -76,6 +77,8 @@ class ResultC(C.Structure):
         ("barcode", c_int32_p),
         ("fingerprint", c_int32_p),
         ("labels", c_uint8_p),
+        ("span_stride", C.c_int32),
+        ("spans", C.POINTER(C.c_uint16)),
     ]
 
 

@@ -107,7 +107,7 @@ class Batch:
             self.h = C.c_void_p()
 
 
-def _result_to_numpy(res: ResultC, mode, want_labels):
+def _result_to_numpy(res: ResultC, mode, want_labels, want_spans=False):
     n = res.n_reads
 
     def arr(ptr, dt, count=n):
@@ -122,6 +122,8 @@ def _result_to_numpy(res: ResultC, mode, want_labels):
                f_score=arr(res.f_score, np.float32), r_score=arr(res.r_score, np.float32))
     if want_labels:
         out["labels"] = arr(res.labels, np.uint8, n * res.label_stride).reshape(n, res.label_stride)
+    if want_spans and mode == MODE_GET_LABEL:
+        out["spans"] = arr(res.spans, np.uint16, n * res.span_stride * 2).reshape(n, res.span_stride, 2)
     if mode == MODE_GET_LABEL:
         out.update(read_type=arr(res.read_type, np.int32), barcode=arr(res.barcode, np.int32),
                    fingerprint=arr(res.fingerprint, np.int32), extracted=arr(res.extracted, np.uint8))
@@ -149,20 +151,21 @@ class Context:
         return Batch(self, max_reads, max_len)
 
     @staticmethod
-    def _params(threshold, minlen, matchstart, matchend, dust, want_labels):
-        return RunParamsC(float(threshold), int(minlen), int(matchstart), int(matchend), int(dust), int(want_labels))
+    def _params(threshold, minlen, matchstart, matchend, dust, want_labels, want_spans=False):
+        return RunParamsC(float(threshold), int(minlen), int(matchstart), int(matchend), int(dust), int(want_labels),
+                          int(want_spans))
 
     def submit(self, model, batch, mode, *, threshold=0.0, minlen=16, matchstart=-1, matchend=-1, dust=100,
-               want_labels=True):
-        rp = self._params(threshold, minlen, matchstart, matchend, dust, want_labels)
+               want_labels=True, want_spans=False):
+        rp = self._params(threshold, minlen, matchstart, matchend, dust, want_labels, want_spans)
         _check(self.lib, self.lib.tdg_submit(self.h, model.h, mode, C.byref(rp), batch.h))
-        batch._pending = (mode, want_labels or mode == MODE_GET_LABEL)
+        batch._pending = (mode, bool(want_labels), bool(want_spans))
 
     def wait(self, batch, copy=True):
         res = ResultC()
         _check(self.lib, self.lib.tdg_wait(batch.h, C.byref(res)))
-        mode, wl = batch._pending
-        return _result_to_numpy(res, mode, wl) if copy else res
+        mode, wl, ws = batch._pending
+        return _result_to_numpy(res, mode, wl, ws) if copy else res
 
     def run_phmm(self, model, batch, mode, **kw):
         """run_pHMM(ab=0, mb, ri, param, 0, numseq, mode) for MODE_GET_LABEL / MODE_GET_PROB."""
@@ -185,7 +188,9 @@ class Context:
 
     def decode_resident(self, model, batch, mode, stream=0, **kw):
         rp = self._params(kw.get("threshold", 0.0), kw.get("minlen", 16), kw.get("matchstart", -1),
-                          kw.get("matchend", -1), kw.get("dust", 100), kw.get("want_labels", True))
+                          kw.get("matchend", -1), kw.get("dust", 100), kw.get("want_labels", True),
+                          kw.get("want_spans", False))
+        batch._resident_spans = bool(kw.get("want_spans", False))
         nl = C.c_int(0)
         _check(self.lib, self.lib.tdg_decode_resident(self.h, model.h, mode, C.byref(rp), batch.h,
                                                       C.c_void_p(stream), C.byref(nl)))
@@ -194,7 +199,7 @@ class Context:
     def download(self, batch, mode=MODE_GET_LABEL):
         res = ResultC()
         _check(self.lib, self.lib.tdg_batch_download(batch.h, C.byref(res)))
-        return _result_to_numpy(res, mode, True)
+        return _result_to_numpy(res, mode, True, getattr(batch, "_resident_spans", False))
 
     def profile_enable(self, on=True):
         _check(self.lib, self.lib.tdg_profile_enable(self.h, 1 if on else 0))

@@ -93,6 +93,9 @@ struct KArgs {
 	float* b_score; float* f_score; float* r_score; float* bar_prob; float* mapq;
 	int32_t* read_type; int32_t* barcode; int32_t* fingerprint; uint8_t* extracted;
 	uint8_t* labels; int32_t label_stride;
+	int32_t store_labels;      // 1: the label row is an output (flushed to `labels`); 0: labels are working storage only
+	uint16_t* spans;           // [read][span_stride] (start, len) pairs of the R-labelled runs of extracted reads, or NULL
+	int32_t span_stride;       // pairs per read (R segments + 1)
 	int32_t dust;              // param->dust, 0 = off
 	// label-DP tables (device)
 	const int32_t* dp_src;     // [H][kMaxSources] source code: >=0 single hmm index, <0 = -(segment+1), INT_MIN = none

@@ -104,6 +104,10 @@ struct DeviceCtx {
 
 struct tdg_context {
 	std::vector<DeviceCtx> devs;
+	// staging batches handed back by the streaming layer: creating and, above all, freeing pinned staging costs more
+	// than a whole chunk of work, so they are kept for the next job and only released by tdg_shutdown
+	std::mutex pool_mu;
+	std::vector<tdg_batch*> pool;
 };
 
 extern "C" int tdg_device_count(const tdg_context* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
@@ -160,6 +164,8 @@ extern "C" int tdg_init(int n_devices, const int* device_ids, tdg_context** out)
 extern "C" void tdg_shutdown(tdg_context* ctx)
 {
 	if (!ctx) return;
+	for (tdg_batch* b : ctx->pool) tdg_batch_destroy(b);
+	ctx->pool.clear();
 	for (auto& d : ctx->devs) {
 		cudaSetDevice(d.dev);
 		cudaStreamSynchronize(d.compute);
@@ -570,6 +576,7 @@ struct Shard {  // one device's part of a batch
 	float *mapq = nullptr, *bar_prob = nullptr, *f = nullptr, *b = nullptr, *r = nullptr;
 	int32_t *read_type = nullptr, *barcode = nullptr, *fingerprint = nullptr;
 	uint8_t *extracted = nullptr, *labels = nullptr;
+	uint16_t* spans = nullptr;
 };
 
 struct tdg_batch {
@@ -581,8 +588,11 @@ struct tdg_batch {
 	float *h_mapq = nullptr, *h_bar_prob = nullptr, *h_f = nullptr, *h_b = nullptr, *h_r = nullptr;
 	int32_t *h_read_type = nullptr, *h_barcode = nullptr, *h_fingerprint = nullptr;
 	uint8_t *h_extracted = nullptr, *h_labels = nullptr;
+	uint16_t* h_spans = nullptr;
+	int span_cap = 0;      // pairs per read the span buffers were allocated for
+	int span_stride = 0;   // pairs per read of the last submit
 	std::vector<Shard> shard;
-	int pending_mode = 0; bool pending = false, want_labels = false;
+	int pending_mode = 0; bool pending = false, want_labels = false, want_spans = false;
 };
 
 struct Carver {  // 256-byte aligned offsets into one slab
@@ -605,6 +615,7 @@ extern "C" void tdg_batch_destroy(tdg_batch* b)
 		cudaStreamSynchronize(b->ctx->devs[k].compute);
 		cudaFree(s.slab);
 		cudaFree(s.labels);
+		cudaFree(s.spans);
 		if (s.h2d_done) cudaEventDestroy(s.h2d_done);
 		if (s.k_done) cudaEventDestroy(s.k_done);
 		if (s.d2h_done) cudaEventDestroy(s.d2h_done);
@@ -612,6 +623,7 @@ extern "C" void tdg_batch_destroy(tdg_batch* b)
 	}
 	cudaFreeHost(b->h_slab);
 	cudaFreeHost(b->h_labels);
+	cudaFreeHost(b->h_spans);
 	delete b;
 }
 
@@ -887,9 +899,12 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	Shard& s = b->shard[devk];
 	if (s.n == 0) return 0;
 	const bool bwd_only = (mode == TDG_MODE_ARCH_COMP);
-	const bool want_labels = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p && p->want_labels);
+	const bool want_labels = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p && p->want_labels);  // run the label DP
 	KArgs a;
 	fill_model_args(a, m, devk, d);
+	a.store_labels = (p && p->want_labels) ? 1 : 0;
+	const bool want_spans = (mode == TDG_MODE_GET_LABEL && p && p->want_spans && s.spans);
+	a.span_stride = want_spans ? b->span_stride : 0;
 	carve_scratch(a, m, d, !bwd_only, wave_ctas);
 	a.words = b->words;
 	a.win_start = 0; a.win_len = -1;
@@ -927,6 +942,7 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 		a.read_type = s.read_type + w0; a.barcode = s.barcode + w0; a.fingerprint = s.fingerprint + w0;
 		a.extracted = s.extracted + w0;
 		a.labels = s.labels + (size_t)w0 * b->label_stride;
+		a.spans = want_spans ? s.spans + (size_t)w0 * b->span_stride * 2 : nullptr;
 		const int ctas = (nw + kBlock - 1) / kBlock;
 		int e;
 		prof_mark(d, 0, stream);
@@ -953,22 +969,47 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	return launches;
 }
 
-static int ensure_label_buffers(tdg_batch* b)
+// Device label rows: working storage of the label DP whenever it runs (the kernel stages them in shared memory when they fit,
+// but that is decided per launch).  Pinned host rows: only when the caller wants the rows back -- pinning them is the slow part.
+static int ensure_label_buffers(tdg_batch* b, bool host_rows)
 {
-	if (b->h_labels) return TDG_OK;
 	int rc;
-	if ((rc = pinned(&b->h_labels, (size_t)b->max_reads * b->label_stride))) return rc;
 	for (size_t k = 0; k < b->shard.size(); k++) {
+		if (b->shard[k].labels) continue;
 		CK(cudaSetDevice(b->ctx->devs[k].dev));
 		if ((rc = devalloc(&b->shard[k].labels, (size_t)b->shard[k].cap * b->label_stride))) return rc;
 	}
+	if (host_rows && !b->h_labels && (rc = pinned(&b->h_labels, (size_t)b->max_reads * b->label_stride))) return rc;
+	return TDG_OK;
+}
+
+static int span_stride_of(const tdg_model* m)
+{
+	int n = 1;
+	for (int s = 0; s < m->hm.S; s++) n += m->hm.seg_type[s] == 'R';
+	return n;
+}
+
+static int ensure_span_buffers(tdg_batch* b, int stride)
+{
+	b->span_stride = stride;
+	if (b->span_cap >= stride) return TDG_OK;
+	int rc;
+	for (size_t k = 0; k < b->shard.size(); k++) {
+		CK(cudaSetDevice(b->ctx->devs[k].dev));
+		if (b->shard[k].spans) { CK(cudaStreamSynchronize(b->shard[k].copy)); CK(cudaFree(b->shard[k].spans)); b->shard[k].spans = nullptr; }
+		if ((rc = devalloc(&b->shard[k].spans, (size_t)b->shard[k].cap * stride * 2))) return rc;
+	}
+	if (b->h_spans) { CK(cudaFreeHost(b->h_spans)); b->h_spans = nullptr; }
+	if ((rc = pinned(&b->h_spans, (size_t)b->max_reads * stride * 2))) return rc;
+	b->span_cap = stride;
 	return TDG_OK;
 }
 
 extern "C" int tdg_batch_reserve_labels(tdg_batch* b)
 {
 	if (!b) return fail(TDG_EINVAL, "NULL batch");
-	return ensure_label_buffers(b);
+	return ensure_label_buffers(b, true);
 }
 
 static int check_compat(tdg_model* m, tdg_batch* b, const tdg_run_params* p)
@@ -998,7 +1039,7 @@ static int upload_shard(tdg_batch* b, int k, cudaStream_t st)
 	return TDG_OK;
 }
 
-static int download_shard(tdg_batch* b, int k, cudaStream_t st, int mode, bool want_labels)
+static int download_shard(tdg_batch* b, int k, cudaStream_t st, int mode, bool want_labels, bool want_spans = false)
 {
 	Shard& s = b->shard[k];
 	if (s.n == 0) return TDG_OK;
@@ -1010,6 +1051,8 @@ static int download_shard(tdg_batch* b, int k, cudaStream_t st, int mode, bool w
 	CK(cudaMemcpyAsync(b->h_f + f, s.f, n * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->h_r + f, s.r, n * 4, cudaMemcpyDeviceToHost, st));
 	if (want_labels && b->h_labels) CK(cudaMemcpyAsync(b->h_labels + f * b->label_stride, s.labels, n * b->label_stride, cudaMemcpyDeviceToHost, st));
+	if (mode == TDG_MODE_GET_LABEL && want_spans && b->h_spans)
+		CK(cudaMemcpyAsync(b->h_spans + f * b->span_stride * 2, s.spans, n * b->span_stride * 2 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
 	if (mode == TDG_MODE_GET_LABEL) {
 		CK(cudaMemcpyAsync(b->h_read_type + f, s.read_type, n * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(b->h_barcode + f, s.barcode, n * 4, cudaMemcpyDeviceToHost, st));
@@ -1025,7 +1068,10 @@ static void fill_result(tdg_batch* b, tdg_result* out)
 	out->n_reads = b->n; out->label_stride = b->label_stride;
 	out->mapq = b->h_mapq; out->bar_prob = b->h_bar_prob; out->f_score = b->h_f; out->b_score = b->h_b; out->r_score = b->h_r;
 	out->read_type = b->h_read_type; out->extracted = b->h_extracted; out->barcode = b->h_barcode;
-	out->fingerprint = b->h_fingerprint; out->labels = b->h_labels;
+	out->fingerprint = b->h_fingerprint;
+	out->labels = b->want_labels ? b->h_labels : nullptr;
+	out->span_stride = b->want_spans ? b->span_stride : 0;
+	out->spans = b->want_spans ? b->h_spans : nullptr;
 }
 
 extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_params* p, tdg_batch* b)
@@ -1039,8 +1085,11 @@ extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_ru
 	if (rc) return rc;
 	if (b->pending) return fail(TDG_EINVAL, "batch already submitted; call tdg_wait first");
 	assign_shards(b);
-	const bool want_labels = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p->want_labels);
-	if (want_labels && (rc = ensure_label_buffers(b))) return rc;
+	const bool run_dp = (mode == TDG_MODE_GET_LABEL) || (mode == TDG_MODE_GET_PROB && p->want_labels);
+	const bool want_labels = mode != TDG_MODE_ARCH_COMP && p->want_labels;   // label rows come back to the host
+	const bool want_spans = mode == TDG_MODE_GET_LABEL && p->want_spans;
+	if (run_dp && (rc = ensure_label_buffers(b, want_labels))) return rc;
+	if (want_spans && (rc = ensure_span_buffers(b, span_stride_of(m)))) return rc;
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
 		DeviceCtx& d = ctx->devs[k];
 		Shard& s = b->shard[k];
@@ -1054,10 +1103,10 @@ extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_ru
 		if (queue_decode(ctx, m, mode, p, b, (int)k, d.compute, nullptr, wc) < 0) return TDG_ECUDA;
 		CK(cudaEventRecord(s.k_done, d.compute));
 		CK(cudaStreamWaitEvent(s.copy, s.k_done, 0));
-		if ((rc = download_shard(b, (int)k, s.copy, mode, want_labels))) return rc;
+		if ((rc = download_shard(b, (int)k, s.copy, mode, want_labels, want_spans))) return rc;
 		CK(cudaEventRecord(s.d2h_done, s.copy));
 	}
-	b->pending = true; b->pending_mode = mode; b->want_labels = want_labels;
+	b->pending = true; b->pending_mode = mode; b->want_labels = want_labels; b->want_spans = want_spans;
 	return TDG_OK;
 }
 
@@ -1173,7 +1222,9 @@ extern "C" int tdg_decode_resident(tdg_context* ctx, tdg_model* m, int mode, con
 	std::lock_guard<std::mutex> model_lock(g_model_mu);
 	int rc = check_compat(m, b, p);
 	if (rc) return rc;
-	if (mode != TDG_MODE_ARCH_COMP && (rc = ensure_label_buffers(b))) return rc;
+	if (mode != TDG_MODE_ARCH_COMP && (rc = ensure_label_buffers(b, true))) return rc;
+	if (mode == TDG_MODE_GET_LABEL && p && p->want_spans && (rc = ensure_span_buffers(b, span_stride_of(m)))) return rc;
+	b->want_labels = true; b->want_spans = (mode == TDG_MODE_GET_LABEL && p && p->want_spans);
 	int total = 0;
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
 		DeviceCtx& d = ctx->devs[k];
@@ -1198,7 +1249,7 @@ extern "C" int tdg_batch_download(tdg_batch* b, tdg_result* out)
 		if (b->shard[k].n == 0) continue;
 		CK(cudaSetDevice(b->ctx->devs[k].dev));
 		CK(cudaDeviceSynchronize());
-		int rc = download_shard(b, (int)k, b->shard[k].copy, TDG_MODE_GET_LABEL, true);
+		int rc = download_shard(b, (int)k, b->shard[k].copy, TDG_MODE_GET_LABEL, true, b->want_spans);
 		if (rc) return rc;
 		CK(cudaStreamSynchronize(b->shard[k].copy));
 	}
@@ -1213,3 +1264,61 @@ extern "C" double tdg_batch_cells(const tdg_model* m, const tdg_batch* b)
 	for (int i = 0; i < b->n; i++) cells += 2.0 * (double)b->h_len[i] * (double)m->hm.C;
 	return cells;
 }
+
+// ---- internal helpers of the streaming layer (tdg_stream.cpp) ---------------------------------------
+namespace tdg {
+
+// A pooled batch that is large enough (and not more than twice too large), or a new one.
+int batch_acquire(tdg_context* ctx, int max_reads, int max_len, tdg_batch** out)
+{
+	{
+		std::lock_guard<std::mutex> l(ctx->pool_mu);
+		for (size_t k = 0; k < ctx->pool.size(); k++) {
+			tdg_batch* b = ctx->pool[k];
+			if (b->max_reads >= max_reads && b->max_len >= max_len && b->max_reads <= 2 * ((max_reads + 31) / 32 * 32) && b->max_len <= 2 * max_len + 16) {
+				ctx->pool.erase(ctx->pool.begin() + (long)k);
+				b->n = 0; b->pending = false;
+				*out = b;
+				return TDG_OK;
+			}
+		}
+	}
+	return tdg_batch_create(ctx, max_reads, max_len, out);
+}
+
+void batch_release(tdg_batch* b)
+{
+	if (!b) return;
+	if (b->pending) { tdg_result r; tdg_wait(b, &r); }
+	std::lock_guard<std::mutex> l(b->ctx->pool_mu);
+	b->ctx->pool.push_back(b);
+}
+
+// Everything the first tdg_submit(MODE_GET_LABEL, want_spans) of `b` under `m` would otherwise allocate on the GPU thread
+// while kernels of earlier chunks are running (cudaMalloc waits for them): device label rows, span buffers.
+int batch_prepare(tdg_batch* b, const tdg_model* m, bool host_labels)
+{
+	int rc = ensure_label_buffers(b, host_labels);
+	if (!rc) rc = ensure_span_buffers(b, span_stride_of(m));
+	return rc;
+}
+
+// The scratch arena of every device for full waves of `m`, allocated on one host thread per device.
+int scratch_prepare(tdg_context* ctx, tdg_model* m)
+{
+	std::vector<std::thread> th;
+	std::vector<int> rcs(ctx->devs.size(), TDG_OK);
+	std::lock_guard<std::mutex> model_lock(g_model_mu);
+	for (size_t k = 0; k < ctx->devs.size(); k++)
+		th.emplace_back([&, k] {
+			DeviceCtx& d = ctx->devs[k];
+			if (cudaSetDevice(d.dev) != cudaSuccess) { rcs[k] = TDG_ECUDA; return; }
+			const int wc = plan_wave_ctas(m, d, true, d.ctas * kBlock);
+			rcs[k] = ensure_scratch(d, scratch_need(m, true, wc));
+		});
+	for (auto& t : th) t.join();
+	for (int rc : rcs) if (rc) return rc;
+	return TDG_OK;
+}
+
+}  // namespace tdg

@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 	auto lab_set = [&](int i, int v) { if (lsm) slab[(size_t)i * bs] = (uint8_t)v; else labels[i] = (uint8_t)v; };
 	auto lab_get = [&](int i) -> int { return lsm ? (int)slab[(size_t)i * bs] : (int)labels[i]; };
 	auto lab_flush = [&](int n) {  // n labels -> global row (label_stride is a multiple of 8, rows are 8-byte aligned)
-		if (!lsm) return;
+		if (!lsm || !a.store_labels) return;
 		for (int i = 0; i < n; i += 4) {
 			uint32_t w = 0;
 #pragma unroll
@@ -1199,6 +1199,23 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 		double s = (double)si;
 		s = s / (double)(c - 3) * 10.0;
 		if (s > (double)a.dust) read_type = 6;
+	}
+	// R-run spans: what make_extracted_read (:3325-3356) keeps of an extracted read -- residue j stays when the segment of
+	// labels[j+1] is an R segment, everything else becomes the spacer.  Labels are non-decreasing in the HMM index (T is
+	// upper triangular), so every R segment yields at most one run, plus one for a label-0 tail behind a -start/-end window.
+	if (a.spans) {
+		uint16_t* sp = a.spans + (size_t)read * a.span_stride * 2;
+		int k = 0;
+		if (extracted) {
+			int j = 0;
+			while (j < rlen && k < a.span_stride) {
+				while (j < rlen && s_stype[s_hlabel[lab_get(j + 1)] & 0xFFFF] != 'R') j++;
+				const int s0 = j;
+				while (j < rlen && s_stype[s_hlabel[lab_get(j + 1)] & 0xFFFF] == 'R') j++;
+				if (j > s0) { sp[2 * k] = (uint16_t)s0; sp[2 * k + 1] = (uint16_t)(j - s0); k++; }
+			}
+		}
+		for (; k < a.span_stride; ++k) { sp[2 * k] = 0; sp[2 * k + 1] = 0; }
 	}
 	a.extracted[read] = extracted ? 1 : 0;
 	a.read_type[read] = read_type;

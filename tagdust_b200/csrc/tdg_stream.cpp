@@ -40,7 +40,12 @@
 #include "tdg_device.h"
 
 namespace tdg {
-int set_last_error(int code, const char* msg);  // tdg_host.cu
+// tdg_host.cu
+int set_last_error(int code, const char* msg);
+int batch_acquire(tdg_context* ctx, int max_reads, int max_len, tdg_batch** out);
+void batch_release(tdg_batch* b);
+int batch_prepare(tdg_batch* b, const tdg_model* m, bool host_labels);
+int scratch_prepare(tdg_context* ctx, tdg_model* m);
 }
 
 namespace {
@@ -142,7 +147,9 @@ struct ParsedChunk {
 	RawVec<uint8_t> codes, qual;
 	RawVec<char> names;
 	// line table of the sequential pass: offsets into `text`, piece lengths (without the newline)
-	struct Rec { uint64_t name, seq, qual; uint32_t name_n, seq_n, qual_n; uint8_t has_seq, has_qual; };
+	// `next`: text offset right behind the line that completed the entry (the first quality line of a FASTQ entry, the first
+	// sequence line of a FASTA entry) -- where a chunk ends when this is its last entry (io.c:1797-1808)
+	struct Rec { uint64_t name, seq, qual, next; uint32_t name_n, seq_n, qual_n; uint8_t has_seq, has_qual; };
 	RawVec<Rec> recs;
 	// the text the line table points into: the reader's mapping (plain files) or a buffer owned by
 	// this chunk (pipes), so that the line pass of the next chunk can run while this one is converted
@@ -161,6 +168,7 @@ struct tdg_fastq {
 	size_t beg = 0, end = 0;   // plain file: unconsumed part [beg, end) of the mapping
 	bool eof = false;
 	int set = 0, seq_p = 0;    // read_fasta_fastq's flags; they persist across chunks like the FILE position does
+	double bytes_per_entry = 0;  // running estimate (plain files): sizes the window the parallel line pass looks at
 	ParsedChunk own;           // storage behind the public tdg_fastq_next
 };
 
@@ -235,12 +243,76 @@ extern "C" void tdg_fastq_close(tdg_fastq* f)
 	delete f;
 }
 
-// Sequential pass: split lines, run read_fasta_fastq's state machine, fill pc.recs.
-static int split_lines(tdg_fastq* f, int max_reads, ParsedChunk& pc)
+// ------------------------------------------------------------------------------------------
+// line pass: read_fasta_fastq's state machine (io.c:1697-1796) over the text
+// ------------------------------------------------------------------------------------------
+// One fgets() piece starting at `pos`: up to the newline, or kMaxLine-1 characters of a longer line, or the unterminated
+// rest of the input.  Returns false when [pos, end) holds no complete piece yet (pipes: more input is needed).
+static inline bool next_piece(const char* base, size_t pos, size_t end, bool at_eof, size_t* piece, size_t* next)
 {
-	pc.n = 0; pc.max_len = 0; pc.fasta = f->fasta; pc.path = f->path;
-	pc.recs.clear();
-	if (max_reads < 1) return failf(TDG_EINVAL, "max_reads must be >= 1");
+	const char* nl = (pos < end) ? (const char*)memchr(base + pos, '\n', std::min(end - pos, (size_t)kMaxLine - 1)) : nullptr;
+	if (nl) { *piece = (size_t)(nl - (base + pos)); *next = pos + *piece + 1; return true; }
+	if (end - pos >= (size_t)kMaxLine - 1) { *piece = kMaxLine - 1; *next = pos + *piece; return true; }  // fgets() splits long lines
+	if (at_eof && pos < end) { *piece = end - pos; *next = end; return true; }  // last line without newline
+	return false;
+}
+
+// What one piece does to the machine: 1 = starts an entry ('@' / '>' with the flag clear), 2 = sequence line of the current
+// entry, 3 = quality line of the current entry, 0 = nothing ('+' header, or a line the reference ignores).
+struct LineState { int set, seq_p; };
+static inline int line_step(LineState& st, const char* base, size_t pos, size_t piece)
+{
+	const char c0 = piece ? base[pos] : '\n';
+	if ((c0 == '@' || c0 == '>') && !st.set) { st.seq_p = 1; st.set = 1; return 1; }
+	if (c0 == '+' && !st.set) { st.seq_p = 0; st.set = 1; return 0; }
+	const int ev = st.set ? (st.seq_p ? 2 : 3) : 0;
+	st.set = 0;
+	return ev;
+}
+static inline bool same_state(const LineState& a, const LineState& b) { return a.set == b.set && (!a.set || a.seq_p == b.seq_p); }
+
+// The entries of one stretch of text plus the data lines that precede its first header ("orphans": they belong to the
+// entry that was open when the stretch began).
+struct SplitOut {
+	RawVec<ParsedChunk::Rec> recs;
+	struct Orphan { uint64_t pos, next; uint32_t n; uint8_t kind; };
+	Orphan orphan[4]; int n_orphan = 0;
+	bool dup = false;       // an entry received a second sequence / quality line: the sequential pass must decide where the chunk ends
+	bool overflow = false;  // more orphans than fit (malformed input)
+	void clear() { recs.clear(); n_orphan = 0; dup = false; overflow = false; }
+	inline void apply(int ev, size_t pos, size_t piece, size_t next, bool fasta)
+	{
+		if (ev == 1) {
+			ParsedChunk::Rec r;
+			memset(&r, 0, sizeof r);
+			r.name = pos; r.name_n = (uint32_t)piece;
+			recs.push_back(r);
+		} else if (ev) {
+			if (recs.empty()) {
+				if (n_orphan < 4) { orphan[n_orphan].pos = pos; orphan[n_orphan].next = next; orphan[n_orphan].n = (uint32_t)piece; orphan[n_orphan].kind = (uint8_t)ev; n_orphan++; }
+				else overflow = true;
+				return;
+			}
+			assign(recs.back(), ev, pos, piece, next, fasta, dup);
+		}
+	}
+	static inline void assign(ParsedChunk::Rec& r, int ev, size_t pos, size_t piece, size_t next, bool fasta, bool& dup)
+	{
+		if (ev == 2) {
+			if (r.has_seq) dup = true;
+			if (fasta && !r.has_seq) r.next = next;
+			r.seq = pos; r.seq_n = (uint32_t)piece; r.has_seq = 1;
+		} else {
+			if (r.has_qual) dup = true;
+			if (!fasta && !r.has_qual) r.next = next;
+			r.qual = pos; r.qual_n = (uint32_t)piece; r.has_qual = 1;
+		}
+	}
+};
+
+// Sequential pass (pipes, and the fallback of the parallel pass): split lines, run the machine, fill pc.recs.
+static int split_lines_serial(tdg_fastq* f, int max_reads, ParsedChunk& pc)
+{
 	size_t pos, end;
 	if (f->pipe) {  // start from what the previous chunk left over
 		pc.own_text.clear();
@@ -253,45 +325,33 @@ static int split_lines(tdg_fastq* f, int max_reads, ParsedChunk& pc)
 		pc.text = f->map;
 		pos = f->beg; end = f->end;
 	}
-	bool done = false;
+	LineState st = {f->set, f->seq_p};
+	bool done = false, dup = false;
 	while (!done) {
 		const char* base = f->pipe ? pc.own_text.data() : f->map;
-		const char* nl = (pos < end) ? (const char*)memchr(base + pos, '\n', std::min(end - pos, (size_t)kMaxLine - 1)) : nullptr;
 		size_t piece, next;
-		if (nl) { piece = (size_t)(nl - (base + pos)); next = pos + piece + 1; }
-		else if (end - pos >= (size_t)kMaxLine - 1) { piece = kMaxLine - 1; next = pos + piece; }  // fgets() splits long lines
-		else if (!f->eof) {
+		if (!next_piece(base, pos, end, f->eof, &piece, &next)) {
+			if (f->eof) break;
 			size_t added = 0;
 			int rc = reader_fill(f, pc, &added);
 			if (rc) return rc;
 			end = pc.own_text.size();
 			continue;
 		}
-		else if (pos < end) { piece = end - pos; next = end; }  // last line without newline
-		else break;
-		const char c0 = piece ? base[pos] : '\n';
-		if ((c0 == '@' || c0 == '>') && !f->set) {
+		const int ev = line_step(st, base, pos, piece);
+		if (ev == 1) {
 			ParsedChunk::Rec r;
 			memset(&r, 0, sizeof r);
 			r.name = pos; r.name_n = (uint32_t)piece;
 			pc.recs.push_back(r);
-			f->seq_p = 1; f->set = 1;
-		} else if (c0 == '+' && !f->set) {
-			f->seq_p = 0; f->set = 1;
-		} else {
-			if (f->set && !pc.recs.empty()) {
-				ParsedChunk::Rec& r = pc.recs.back();
-				if (f->seq_p) { r.seq = pos; r.seq_n = (uint32_t)piece; r.has_seq = 1; }
-				else { r.qual = pos; r.qual_n = (uint32_t)piece; r.has_qual = 1; }
-			}
-			f->set = 0;
-		}
+		} else if (ev && !pc.recs.empty()) SplitOut::assign(pc.recs.back(), ev, pos, piece, next, f->fasta, dup);
 		pos = next;
 		if ((int)pc.recs.size() == max_reads) {  // io.c:1797-1808: the chunk ends once its last entry is complete
 			const ParsedChunk::Rec& r = pc.recs.back();
 			if ((!f->fasta && r.has_qual) || (f->fasta && r.has_seq)) done = true;
 		}
 	}
+	f->set = st.set; f->seq_p = st.seq_p;
 	if (f->pipe) {
 		pc.text = pc.own_text.data();
 		f->carry.resize(end - pos);
@@ -301,6 +361,146 @@ static int split_lines(tdg_fastq* f, int max_reads, ParsedChunk& pc)
 	}
 	pc.n = (int)pc.recs.size();
 	return TDG_OK;
+}
+
+// Parallel pass over a memory-mapped file.  The text is cut at line starts into one stretch per thread.  A thread does not
+// know the machine's state at its first line, so it runs the three possible states (flag clear; flag set expecting a
+// sequence line; flag set expecting a quality line) side by side until they agree -- which takes a handful of lines, because
+// every data line clears the flag -- keeps what each of them produced up to there, and runs one machine from there on.
+// The stretches are then stitched in order: the state the previous stretch ended in selects the prefix that was right.
+// Returns 1 when the chunk was produced, 0 when the caller has to use the sequential pass (malformed or unusual input:
+// an entry with two sequence / quality lines, a last entry that is not complete, stretches that never agree).
+struct SplitPart {
+	SplitOut pre[3], rest;
+	LineState pre_end[3], end_state;
+	bool converged = false;
+	size_t beg = 0, end = 0;
+};
+
+static int split_lines_parallel(tdg_fastq* f, int max_reads, int threads, ParsedChunk& pc, std::vector<SplitPart>& parts)
+{
+	const char* base = f->map;
+	const size_t file_end = f->end;
+	const bool fasta = f->fasta;
+	pc.text = base;
+	size_t pos = f->beg;
+	LineState st = {f->set, f->seq_p};
+	bool dup = false;
+	const int T = std::max(1, threads);
+	if ((int)parts.size() < T) parts.resize((size_t)T);
+	while ((int)pc.recs.size() < max_reads && pos < file_end) {
+		// window: what the missing entries should need, a little more, at least 1 MB
+		const double bpe = f->bytes_per_entry > 0 ? f->bytes_per_entry : 512.0;
+		size_t want = (size_t)((double)(max_reads - (int)pc.recs.size()) * bpe * 1.02) + ((size_t)1 << 20);
+		size_t wend = (file_end - pos <= want) ? file_end : pos + want;
+		if (wend < file_end) {  // cut behind a newline
+			const char* nl = (const char*)memchr(base + wend, '\n', file_end - wend);
+			wend = nl ? (size_t)(nl - base) + 1 : file_end;
+		}
+		const size_t wbytes = wend - pos;
+		const int P = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, wbytes >> 18));  // >= 256 KB per stretch
+		for (int k = 0; k < P; k++) {
+			size_t b = pos + wbytes * (size_t)k / (size_t)P;
+			if (k > 0) {
+				const char* nl = (b < wend) ? (const char*)memchr(base + b - 1, '\n', wend - (b - 1)) : nullptr;
+				b = nl ? (size_t)(nl - base) + 1 : wend;
+			}
+			parts[k].beg = b;
+		}
+		for (int k = 0; k < P; k++) parts[k].end = (k + 1 < P) ? parts[k + 1].beg : wend;
+		parallel_for(P, (size_t)P, 0, [&](size_t kb, size_t ke, int) {
+			for (size_t k = kb; k < ke; k++) {
+				SplitPart& sp = parts[k];
+				for (auto& o : sp.pre) o.clear();
+				sp.rest.clear();
+				sp.converged = false;
+				const bool last_part = sp.end == file_end;  // only there can a line lack its newline
+				LineState h[3] = {{0, 0}, {1, 1}, {1, 0}};
+				size_t p = sp.beg, piece, next;
+				int lines = 0;
+				while (!(same_state(h[0], h[1]) && same_state(h[0], h[2]))) {
+					if (lines++ >= 64 || !next_piece(base, p, sp.end, last_part, &piece, &next)) break;
+					for (int q = 0; q < 3; q++) sp.pre[q].apply(line_step(h[q], base, p, piece), p, piece, next, fasta);
+					p = next;
+				}
+				for (int q = 0; q < 3; q++) sp.pre_end[q] = h[q];
+				if (!(same_state(h[0], h[1]) && same_state(h[0], h[2]))) { sp.end_state = h[0]; continue; }  // stitched serially
+				sp.converged = true;
+				LineState c = h[0];
+				SplitOut& out = sp.rest;
+				out.recs.reserve((size_t)((double)(sp.end - p) / bpe * 1.1) + 16);
+				while (next_piece(base, p, sp.end, last_part, &piece, &next)) {
+					out.apply(line_step(c, base, p, piece), p, piece, next, fasta);
+					p = next;
+				}
+				sp.end_state = c;
+			}
+		});
+		// stitch
+		const size_t recs_before = pc.recs.size();
+		auto merge = [&](SplitOut& o) -> bool {
+			if (o.dup || o.overflow) return false;
+			for (int q = 0; q < o.n_orphan; q++)
+				if (!pc.recs.empty()) SplitOut::assign(pc.recs.back(), o.orphan[q].kind, o.orphan[q].pos, o.orphan[q].n, o.orphan[q].next, fasta, dup);
+			if (o.recs.size()) {
+				const size_t at = pc.recs.size();
+				pc.recs.resize(at + o.recs.size());
+				memcpy(pc.recs.data() + at, o.recs.data(), o.recs.size() * sizeof(ParsedChunk::Rec));
+			}
+			return true;
+		};
+		for (int k = 0; k < P; k++) {
+			SplitPart& sp = parts[k];
+			const int q = !st.set ? 0 : (st.seq_p ? 1 : 2);
+			if (!sp.converged) {
+				// the three machines did not agree within the stretch's first lines: run the right one over the whole stretch
+				const bool last_part = sp.end == file_end;
+				SplitOut& out = sp.rest;
+				out.clear();
+				size_t p = sp.beg, piece, next;
+				while (next_piece(base, p, sp.end, last_part, &piece, &next)) {
+					out.apply(line_step(st, base, p, piece), p, piece, next, fasta);
+					p = next;
+				}
+				if (!merge(out)) return 0;
+				continue;
+			}
+			if (!merge(sp.pre[q]) || !merge(sp.rest)) return 0;
+			st = sp.end_state;
+		}
+		if (dup) return 0;
+		if (pc.recs.size() > recs_before) f->bytes_per_entry = (double)wbytes / (double)(pc.recs.size() - recs_before);
+		pos = wend;
+	}
+	if ((int)pc.recs.size() >= max_reads) {
+		const ParsedChunk::Rec& r = pc.recs[(size_t)max_reads - 1];
+		if (!((!fasta && r.has_qual) || (fasta && r.has_seq)) || !r.next) return 0;
+		// the chunk ends behind the line that completed its last entry; that was a data line, so the flag is clear there
+		pc.recs.resize((size_t)max_reads);
+		f->beg = r.next; f->set = 0; f->seq_p = fasta ? 1 : 0;
+	} else {
+		f->beg = pos; f->set = st.set; f->seq_p = st.seq_p;
+	}
+	pc.n = (int)pc.recs.size();
+	return 1;
+}
+
+static int split_lines(tdg_fastq* f, int max_reads, ParsedChunk& pc, int threads = 1, std::vector<SplitPart>* scratch = nullptr)
+{
+	pc.n = 0; pc.max_len = 0; pc.fasta = f->fasta; pc.path = f->path;
+	pc.recs.clear();
+	if (max_reads < 1) return failf(TDG_EINVAL, "max_reads must be >= 1");
+	static const bool no_parallel = getenv("TDG_SERIAL_SPLIT") != nullptr;   // tests: force the sequential pass
+	if (!f->pipe && threads > 1 && !no_parallel && f->end - f->beg >= ((size_t)1 << 20)) {
+		std::vector<SplitPart> local;
+		const size_t beg0 = f->beg;
+		const int set0 = f->set, seq0 = f->seq_p;
+		if (split_lines_parallel(f, max_reads, threads, pc, scratch ? *scratch : local) == 1) return TDG_OK;
+		if (getenv("TDG_TRACE")) fprintf(stderr, "[trace] %s: parallel line pass stepped aside at offset %zu, sequential pass takes this chunk\n", f->path.c_str(), beg0);
+		f->beg = beg0; f->set = set0; f->seq_p = seq0;   // sequential pass from the same place
+		pc.recs.clear();
+	}
+	return split_lines_serial(f, max_reads, pc);
 }
 
 // Conversion pass: names, codes, qualities on the worker pool.
@@ -371,7 +571,7 @@ extern "C" int tdg_fastq_next(tdg_fastq* f, int max_reads, int threads, tdg_fast
 	if (!f || !chunk) return failf(TDG_EINVAL, "tdg_fastq_next: NULL argument");
 	int rc;
 	try {
-		rc = split_lines(f, max_reads, f->own);
+		rc = split_lines(f, max_reads, f->own, threads);
 		if (!rc) rc = convert_chunk(f->own, threads);
 	} catch (const std::bad_alloc&) {
 		rc = failf(TDG_EMEM, "out of host memory while reading %s", f->path.c_str());
@@ -406,7 +606,7 @@ extern "C" int tdg_sequence_stats(const char* path, int fasta, int num_query, co
 	const int64_t target = ((int64_t)1000000 / num_query + 1) * (int64_t)num_query;
 	while (out->total_read < target) {
 		const int want = (int)std::min<int64_t>(target - out->total_read, (int64_t)1 << 20);
-		if ((rc = split_lines(f, want, pc)) || (rc = convert_chunk(pc, T))) break;
+		if ((rc = split_lines(f, want, pc, T)) || (rc = convert_chunk(pc, T))) break;
 		if (pc.n == 0) break;
 		std::vector<Acc> acc((size_t)T);
 		const uint8_t* end_of_codes = pc.codes.data() + pc.codes.size();
@@ -652,11 +852,20 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					Slot& s = slots[k];
 					s.batch_reads[i] = std::min(chunk_reads, 1 << 24);
 					s.batch_len[i] = job->inputs[i].expected_len > 0 ? job->inputs[i].expected_len : job->inputs[i].max_seq_len;
-					if (tdg_batch_create(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK ||
-					    tdg_batch_reserve_labels(s.batch[i]) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
+					// the label rows stay on the device (the writer works from the R-run spans): no pinned label staging
+					if (tdg::batch_acquire(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK ||
+					    tdg::batch_prepare(s.batch[i], job->inputs[i].model, false) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
 					if (getenv("TDG_TRACE")) fprintf(stderr, "[trace] batch for slot %d input %d created in %.3f s\n", k, i, now_s() - ta);
 				});
-	const bool trace = getenv("TDG_TRACE") != nullptr;
+	// the scratch arenas (tens of GB per device) are allocated meanwhile, one thread per device
+	for (int i = 0; i < NI; i++)
+		if (job->inputs[i].model)
+			t_alloc.emplace_back([&, i] {
+				const double ta = now_s();
+				if (tdg::scratch_prepare(ctx, job->inputs[i].model) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
+				if (getenv("TDG_TRACE")) fprintf(stderr, "[trace] scratch for input %d ready in %.3f s\n", i, now_s() - ta);
+			});
+	const bool trace = getenv("TDG_TRACE") != nullptr && getenv("TDG_TRACE")[0] != 0;
 	auto tr = [&](const char* stage, int k, double t0) {
 		if (trace) fprintf(stderr, "[trace] %-8s chunk-slot %d  %.3f -> %.3f s\n", stage, k, t0 - t_start, now_s() - t_start);
 	};
@@ -666,6 +875,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	// ---- stage 1a: line splitting (sequential per file)
 	std::thread t_split([&] {
 		try {
+		std::vector<SplitPart> split_scratch;
 		for (;;) {
 			int k;
 			if (!q_free.pop(k) || sh.failed) break;
@@ -673,7 +883,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			const double t0 = now_s();
 			bool ok = true;
 			for (int i = 0; i < NI && ok; i++)
-				if (split_lines(rd[i], chunk_reads, s.pc[i]) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
+				if (split_lines(rd[i], chunk_reads, s.pc[i], threads, &split_scratch) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
 			for (int i = 0; i + 1 < NI && ok; i++)
 				for (int j = i + 1; j < NI && ok; j++)
 					if (s.pc[i].n != s.pc[j].n) {  // barcode_hmm.c:258-268
@@ -726,7 +936,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 						s.batch[i] = nullptr;
 						s.batch_reads[i] = std::max(s.batch_reads[i], std::max(pc.n, std::min(chunk_reads, 1 << 24)));
 						s.batch_len[i] = std::max(s.batch_len[i], pc.max_len);
-						if (tdg_batch_create(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; break; }
+						if (tdg::batch_acquire(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; break; }
 					}
 					tdg_batch_clear(s.batch[i]);
 					if (tdg_batch_append_ragged(s.batch[i], pc.n, pc.codes.data(), pc.seq_off.data(), pc.len.data(), threads) != TDG_OK) {
@@ -764,6 +974,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			if (sh.failed) break;
 			Slot& s = slots[k];
 			bool ok = true;
+			const double ts = now_s();
 			if (!s.last)
 				for (int i = 0; i < NI && ok; i++) {
 					tdg_model* m = job->inputs[i].model;
@@ -771,10 +982,11 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					tdg_run_params rp;
 					rp.confidence_threshold = job->inputs[i].confidence_threshold;
 					rp.minlen = job->minlen; rp.matchstart = job->matchstart; rp.matchend = job->matchend;
-					rp.dust = job->dust; rp.want_labels = 1;
+					rp.dust = job->dust; rp.want_labels = 0; rp.want_spans = 1;
 					if (tdg_submit(ctx, m, TDG_MODE_GET_LABEL, &rp, s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; }
 				}
 			if (!ok) break;
+			tr("submit", k, ts);
 			if (prev >= 0 && !finish(prev)) { prev = -1; break; }
 			prev = k;
 		}
@@ -801,28 +1013,23 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 				std::vector<int64_t>& tl = tally[t];
 				std::vector<int32_t> rt((size_t)NI), fpv((size_t)NI);
 				std::vector<float> mq((size_t)NI);
+				std::vector<const uint16_t*> spv((size_t)NI);   // R-run spans of an extracted read, nullptr = the whole read
+				std::vector<int> spn((size_t)NI);
 				char fseq[260];
 				for (size_t r = b; r < e; r++) {
-					// per file: read_type / barcode / fingerprint / mapq and the in-place extraction rewrite
+					// per file: read_type / barcode / fingerprint / mapq and what make_extracted_read leaves of the read
 					int merged = -100000, barcode = -1;
 					for (int i = 0; i < NI; i++) {
-						ParsedChunk& pc = s.pc[i];
-						uint8_t* seq = pc.codes.data() + pc.seq_off[r];
-						uint8_t* ql = pc.fasta ? nullptr : pc.qual.data() + pc.seq_off[r];
-						const int len = pc.len[r];
+						const ParsedChunk& pc = s.pc[i];
+						spv[i] = nullptr; spn[i] = 0;
 						if (job->inputs[i].model) {
 							const tdg_result& R = s.res[i];
 							rt[i] = R.read_type[r]; fpv[i] = R.fingerprint[r]; mq[i] = R.mapq[r];
 							if (i == job->barcode_input) barcode = R.barcode[r];
-							if (R.extracted[r]) {  // make_extracted_read: everything outside R segments becomes the spacer 65
-								const uint8_t* lab = R.labels + (size_t)r * R.label_stride;
-								const uint8_t* isr = is_read[i].data();
-								for (int j = 0; j < len; j++)
-									if (!isr[lab[j + 1]]) { seq[j] = 65; if (ql) ql[j] = 65; }
-							}
+							if (R.extracted[r]) { spv[i] = R.spans + r * (size_t)R.span_stride * 2; spn[i] = R.span_stride; }
 						} else {
 							rt[i] = TDG_EXTRACT_SUCCESS; fpv[i] = -1; mq[i] = -1.0f;  // do_rna_dust + clear_read_info (io.c:2063-2093)
-							if (job->dust && dust_low_complexity(seq, len, job->dust)) rt[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
+							if (job->dust && dust_low_complexity(pc.codes.data() + pc.seq_off[r], pc.len[r], job->dust)) rt[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
 						}
 						merged = std::max(merged, rt[i]);
 					}
@@ -845,41 +1052,51 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 						const char* name = pc.names.data() + pc.name_off[r];
 						const size_t name_len = strlen(name);
 						int f = base_file[i] + sel;
-						int g = 0;
-						while (g < len) {
-							while (g < len && seq[g] >= 5) g++;
-							int h = g;
-							while (h < len && seq[h] < 5) h++;
-							if (h == g) break;
-							const bool more = h < len;  // a spacer follows: the next run goes to the next READ file
-							if (f >= 0 && f < num_outfiles && files[f]) {
-								const int run = h - g;
-								char* p = out[f].grow(name_len + 2 * (size_t)run + 320);
-								char* p0 = p;
-								*p++ = '@';
-								memcpy(p, name, name_len); p += name_len;
-								if (fpv[i] != -1) {
-									memcpy(p, ";FP:", 4); p += 4;
-									if (job->print_seq_finger) {  // get_finger_seq, io.c:1018-1029
-										int key = fpv[i];
-										const int fl = key & 0xFF;
-										key >>= 8;
-										for (int q = 0; q < fl; q++) { fseq[fl - q - 1] = "ACGTN"[key & 0x3]; key >>= 2; }
-										memcpy(p, fseq, (size_t)fl); p += fl;
-									} else p = put_int(p, fpv[i]);
+						// print_all (io.c:923-1001) walks the rewritten read: runs of bases (codes < 5) separated by spacers, one
+						// output record per run, the run behind a spacer goes to the next READ file.  Here the spacers are never
+						// written: a residue is "in" when it lies in an R-run span (extracted reads) and is a base.
+						const uint16_t* sp = spv[i];
+						const int nsp = sp ? spn[i] : 1;
+						for (int k = 0; k < nsp; k++) {
+							const int s0 = sp ? (int)sp[2 * k] : 0, sl = sp ? (int)sp[2 * k + 1] : len;
+							if (sl == 0) break;
+							const int s1 = std::min(len, s0 + sl);
+							int g = s0;
+							while (g < s1) {
+								while (g < s1 && seq[g] >= 5) g++;
+								int h = g;
+								while (h < s1 && seq[h] < 5) h++;
+								if (h == g) break;
+								const bool more = h < len;  // something follows the run: the next run goes to the next READ file
+								if (f >= 0 && f < num_outfiles && files[f]) {
+									const int run = h - g;
+									char* p = out[f].grow(name_len + 2 * (size_t)run + 320);
+									char* p0 = p;
+									*p++ = '@';
+									memcpy(p, name, name_len); p += name_len;
+									if (fpv[i] != -1) {
+										memcpy(p, ";FP:", 4); p += 4;
+										if (job->print_seq_finger) {  // get_finger_seq, io.c:1018-1029
+											int key = fpv[i];
+											const int fl = key & 0xFF;
+											key >>= 8;
+											for (int q = 0; q < fl; q++) { fseq[fl - q - 1] = "ACGTN"[key & 0x3]; key >>= 2; }
+											memcpy(p, fseq, (size_t)fl); p += fl;
+										} else p = put_int(p, fpv[i]);
+									}
+									memcpy(p, ";RQ:", 4); p += 4;
+									p += tdg_format_rq(mq[i], p);
+									*p++ = '\n';
+									for (int q = g; q < h; q++) *p++ = alphabet[seq[q]];
+									*p++ = '\n'; *p++ = '+'; *p++ = '\n';
+									if (ql) { memcpy(p, ql + g, (size_t)run); p += run; }
+									else { memset(p, '.', (size_t)run); p += run; }
+									*p++ = '\n';
+									out[f].n += (size_t)(p - p0);
 								}
-								memcpy(p, ";RQ:", 4); p += 4;
-								p += tdg_format_rq(mq[i], p);
-								*p++ = '\n';
-								for (int q = g; q < h; q++) *p++ = alphabet[seq[q]];
-								*p++ = '\n'; *p++ = '+'; *p++ = '\n';
-								if (ql) { memcpy(p, ql + g, (size_t)run); p += run; }
-								else { memset(p, '.', (size_t)run); p += run; }
-								*p++ = '\n';
-								out[f].n += (size_t)(p - p0);
+								if (more) f += nalt;
+								g = h;
 							}
-							if (more) f += nalt;
-							g = h;
 						}
 					}
 				}
@@ -926,9 +1143,8 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	t_write.join();
 	double tq = now_s();
 	{
-		std::vector<std::thread> t_free;
-		for (auto& s : slots) for (auto* b : s.batch) if (b) t_free.emplace_back([b] { tdg_batch_destroy(b); });
-		for (auto& t : t_free) t.join();
+		// back to the context's pool (released by tdg_shutdown): freeing pinned staging costs ~0.3 s per batch
+		for (auto& s : slots) for (auto* b : s.batch) if (b) tdg::batch_release(b);
 	}
 	tr("free-batches", -1, tq); tq = now_s();
 	close_readers();

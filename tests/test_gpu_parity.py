@@ -283,3 +283,57 @@ def test_alternative_kernel_paths_give_the_same_bits(gpu_ctx, oracle, ref, name,
     rep = compare(gpu, ora, lens, MODE_GET_LABEL, name)
     ref.model_free(mb); ref.param_free(p)
     assert all(v == 0 for v in rep.values()), f"{name} with {env}: mismatches {rep}"
+
+
+def spans_from_labels(labels, lens, desc, extracted, stride):
+    """make_extracted_read (barcode_hmm.c:3325-3356) restated on the label rows: the runs of residues j whose
+    labels[j + 1] lies in an R segment."""
+    is_r = np.array([desc.seg_type[int(lab) & 0xFFFF:(int(lab) & 0xFFFF) + 1] == b"R" for lab in desc.label])
+    out = np.zeros((len(lens), stride, 2), np.uint16)
+    for r in range(len(lens)):
+        if not extracted[r]:
+            continue
+        m = is_r[labels[r, 1:lens[r] + 1]]
+        k, j = 0, 0
+        while j < lens[r]:
+            if not m[j]:
+                j += 1
+                continue
+            s = j
+            while j < lens[r] and m[j]:
+                j += 1
+            out[r, k] = (s, j - s)
+            k += 1
+    return out
+
+
+@pytest.mark.parametrize("name", ["b48_r", "p_b_r_p", "o_b_s_r", "f_s_b_r", "p18_b_r_p14"])
+def test_spans_equal_label_rows(gpu_ctx, ref, name):
+    """want_spans: the R-run table the demux writer works from is exactly what the label rows say; and with
+    want_labels=0 (rows stay on the device) every other output keeps its bits."""
+    codes, lens, _ = make_case_reads(name, 1200, seed=23, read_len=60 if name == "b48_r" else None)
+    p, mb, desc = build_ref_model(ref, name)
+    full = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.0, minlen=8, dust=100, want_spans=True)
+    stride = full["spans"].shape[1]
+    assert stride == 1 + sum(1 for t in desc.seg_type if t == ord("R"))
+    want = spans_from_labels(full["labels"], lens, desc, full["extracted"], stride)
+    assert full["extracted"].sum() > 100
+    assert np.array_equal(full["spans"], want)
+    lean = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.0, minlen=8, dust=100, want_labels=False, want_spans=True)
+    assert "labels" not in lean
+    for k in SCORE_KEYS:
+        assert np.array_equal(bits(lean[k]), bits(full[k])), k
+    for k in ("read_type", "barcode", "fingerprint", "extracted", "spans"):
+        assert np.array_equal(lean[k], full[k]), k
+    ref.model_free(mb); ref.param_free(p)
+
+
+def test_spans_with_window(gpu_ctx, ref):
+    """-start/-end: labels behind the window are 0, so an R segment at HMM 0's segment adds a trailing run."""
+    name = "b4_r"
+    codes, lens, _ = make_case_reads(name, 600, seed=29, read_len=40, len_jitter=0)
+    p, mb, desc = build_ref_model(ref, name, max_len=48)
+    out = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=0.5, minlen=8, dust=100, matchstart=0, matchend=30, want_spans=True)
+    want = spans_from_labels(out["labels"], lens, desc, out["extracted"], out["spans"].shape[1])
+    assert np.array_equal(out["spans"], want)
+    ref.model_free(mb); ref.param_free(p)

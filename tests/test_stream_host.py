@@ -123,6 +123,78 @@ def test_reader_matches_reference_reader(tmp_path, variant):
     rd.close()
 
 
+def read_all_chunks(path, chunk, threads):
+    rd = FastqReader(path)
+    out = []
+    while True:
+        try:
+            c = rd.next(chunk, threads=threads)
+        except TagdustError as e:
+            out.append(("error", str(e)))
+            break
+        if c is None:
+            break
+        # only len + 1 bytes of a read's slot are defined (the slot is sized for the raw line, e.g. with its '\r')
+        rows = [(int(o), int(L)) for o, L in zip(c["off"], c["len"])]
+        out.append((c["n"], c["len"].tobytes(), c["off"].tobytes(), b"".join(c["codes"][o:o + L + 1].tobytes() for o, L in rows),
+                    None if c["qual"] is None else b"".join(c["qual"][o:o + L + 1].tobytes() for o, L in rows), tuple(c["names"])))
+    rd.close()
+    return out
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "exotic", "no_trailing_newline", "long_lines", "fasta", "double_plus",
+                                     "truncated", "junk_between"])
+def test_parallel_line_pass_equals_serial(tmp_path, variant):
+    """Files of a few MB go through the multi-threaded line pass (stretches cut at line starts, three start-state
+    hypotheses per stretch, stitched in order); it must hand out exactly the chunks of the sequential pass, which the
+    tests above pin to the reference's read_fasta_fastq -- including malformed input, where it has to step aside."""
+    rng = np.random.default_rng(11)
+    n = 14000
+    path = tmp_path / ("x.fa" if variant == "fasta" else "x.fq")
+    if variant == "fasta":
+        with open(path, "w") as fh:
+            for k in range(n * 2):
+                fh.write(f">seq{k} d\n{'ACGTNNACGT' * (1 + k % 19)}\n")
+                if k % 10 == 0:
+                    fh.write("\n")
+                if k % 25 == 0:
+                    fh.write("GGGGGGGG\n>not a header: the flag is clear, so it IS one\nAC\n")
+    else:
+        recs = random_records(rng, n, exotic=(variant in ("exotic", "junk_between")))
+        if variant == "long_lines":
+            for k in range(0, n, 900):
+                L = 10050 + k
+                recs[k] = (recs[k][0], "ACGT" * (L // 4), "I" * (L // 4 * 4))
+        write_fastq(path, recs, crlf=(variant == "crlf"), trailing_newline=(variant != "no_trailing_newline"))
+        if variant in ("double_plus", "truncated", "junk_between"):
+            txt = open(path).read().split("\n")
+            if variant == "double_plus":      # an entry with two quality blocks, far into the file
+                i = 4 * 9001
+                txt[i + 3:i + 3] = [txt[i + 3], "+"]
+            elif variant == "truncated":      # the last entry has no quality line
+                txt = txt[:-2]
+            else:                             # stray lines between entries, some looking like headers
+                for i in range(4 * 13000, 4 * 100, -4 * 777):
+                    txt[i:i] = ["junk line", "+", "@IIIIIII"]
+            open(path, "w").write("\n".join(txt))
+    assert os.path.getsize(path) > 2 << 20
+    for chunk in (1000, 5003, 100000):
+        serial = read_all_chunks(path, chunk, 1)
+        for threads in (2, 5):
+            par = read_all_chunks(path, chunk, threads)
+            assert len(par) == len(serial)
+            for a, b in zip(par, serial):
+                assert a == b
+    if variant in ("plain", "exotic", "fasta") and have_ref():
+        R = RefReader()
+        rd = FastqReader(path)
+        for k in range(3):
+            mine = rd.next(6000, threads=4)
+            ref = R.chunk(path, 6000, k)
+            assert_chunk_equal(mine, ref)
+        rd.close()
+
+
 def test_reader_fasta_and_blank_lines(tmp_path):
     if not have_ref():
         pytest.skip("oracle/_ref not built")
