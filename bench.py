@@ -466,7 +466,7 @@ def run_gpu_arm(args):
     batches = []
     if rank != 0:
         model.close(); ctx.close()
-    barrier()
+    dist_util.cpu_barrier()   # host-side from here on: an NCCL barrier would park a spinning kernel on the other ranks' GPUs
     if rank == 0 and not args.no_files:
         try:
             ctxN = ctx if world == 1 else Context(n_devices=world)
@@ -491,7 +491,7 @@ def run_gpu_arm(args):
         emit(line)
         model.close()
         ctx.close()
-    barrier()
+    dist_util.cpu_barrier()
     dist_util.finalize()
 
 

@@ -36,6 +36,9 @@ extern "C" {
 #define TDG_MODE_GET_LABEL 1
 #define TDG_MODE_GET_PROB  4
 #define TDG_MODE_ARCH_COMP 5
+/* not a run_pHMM mode: run_rna_dust() (barcode_hmm.c:2043, do_rna_dust :2370) for input files whose architecture is a
+ * single R segment -- every read starts as EXTRACT_SUCCESS, then the -ref artifact filter, then dust; no model */
+#define TDG_MODE_RNA_DUST  6
 
 /* read_type codes: io.h:36-52 (the numbering every reference TU actually sees) */
 #define TDG_EXTRACT_SUCCESS                    0
@@ -55,6 +58,7 @@ enum { TDG_MM = 0, TDG_MI, TDG_MD, TDG_II, TDG_IM, TDG_DD, TDG_DM, TDG_MSKIP, TD
 typedef struct tdg_context tdg_context;
 typedef struct tdg_model   tdg_model;
 typedef struct tdg_batch   tdg_batch;
+typedef struct tdg_refset  tdg_refset;   /* -ref: the artifact sequences (struct fasta, io.h:59-69) on the devices */
 
 /* ------------------------------------------------------------------------------------
  * Flattened `struct model_bag` (barcode_hmm.h:247-272).  Order everywhere is
@@ -92,6 +96,14 @@ typedef struct tdg_run_params {
 	                                 rows on the device -- most of the device->host bytes of a read */
 	int32_t want_spans;           /* 1 (MODE_GET_LABEL): return the R-labelled runs of every extracted read (tdg_result.spans),
 	                                 i.e. what make_extracted_read (barcode_hmm.c:3325-3356) leaves of it */
+	/* -ref artifact filter, match_to_reference (barcode_hmm.c:2478-2583); order extract -> artifacts -> dust (:2345-2354).
+	 * A read within filter_error edits of a reference sequence (either strand) gets read_type = (sequence number << 8) | 5.
+	 * The batch stands for ONE run_pHMM / run_rna_dust call: the reference matches the reads in groups of four per thread
+	 * slice of that call with one Myers variant and the remaining (slice length mod 4) reads with another, so the slicing
+	 * (slice_threads = param->num_threads over the batch's reads) is part of the result. */
+	const tdg_refset* refset;     /* NULL: no artifact filter */
+	int32_t filter_error;         /* param->filter_error (-fe, default 2) */
+	int32_t slice_threads;        /* param->num_threads */
 } tdg_run_params;
 
 /* Per-read results (host arrays owned by the batch; valid after tdg_wait/tdg_run). */
@@ -157,6 +169,12 @@ int  tdg_arch_compile(int num_segments, const char* const* segment_strings,
                       const tdg_arch_params* p, tdg_arch** out);
 const tdg_model_desc* tdg_arch_desc(const tdg_arch* a);
 void tdg_arch_destroy(tdg_arch* a);
+
+/* ---- -ref artifact sequences ---------------------------------------------------------- */
+/* codes = fasta->string (nuc_code[] of every sequence back to back), s_index[numseq + 1] = fasta->s_index
+ * (get_fasta, io.c).  Copied to every device of the context. */
+int  tdg_refset_create(tdg_context* ctx, const uint8_t* codes, const int32_t* s_index, int numseq, tdg_refset** out);
+void tdg_refset_destroy(tdg_refset* r);
 
 /* ---- read batches (pinned, structure-of-arrays, 4-bit packed) ---------------------- */
 /* A batch owns pinned host staging (packed codes, lengths, results) and the matching

@@ -15,8 +15,7 @@
  * of fgets and four mallocs per read, code conversion / 4-bit packing / record formatting on a
  * pool of host threads, output files opened once, and three pipeline stages (parse, GPU, write)
  * running concurrently on different chunks with double-buffered pinned batches.
- * SAM/BAM input and the -ref artifact filter are NOT handled here (the caller keeps the
- * reference's own loop for those).
+ * SAM/BAM input is NOT handled here (the caller keeps the reference's own loop for it).
  */
 #ifndef TAGDUST_B200_STREAM_H
 #define TAGDUST_B200_STREAM_H
@@ -108,6 +107,13 @@ typedef struct tdg_demux_job {
 	int32_t print_seq_finger;          /* param->print_seq_finger (-show_finger_seq) */
 	int32_t threads;                   /* host worker threads (param->num_threads) */
 	int32_t chunk_reads;               /* reads per pipeline chunk; 0 = default */
+	/* -ref artifact filter (param->reference_fasta; match_to_reference barcode_hmm.c:2478-2583).  With a refset every
+	 * pipeline chunk is exactly one chunk of the reference's loop (ref_chunk_reads = param->num_query reads), because the
+	 * reference's result depends on the thread slicing (`threads`) of each run_pHMM / run_rna_dust call. */
+	const tdg_refset* refset;          /* NULL = no artifact filter */
+	int32_t filter_error;              /* param->filter_error */
+	int32_t ref_chunk_reads;           /* param->num_query */
+	int64_t* artifact_counts;          /* out, [sequences of the refset] or NULL: reference_fasta->mer_hash (:381) */
 } tdg_demux_job;
 
 typedef struct tdg_demux_stats {       /* struct log_information, barcode_hmm.c:232-241, :356-384 */

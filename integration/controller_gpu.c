@@ -13,7 +13,8 @@
  * those two dominate the run time by orders of magnitude.
  *
  * Not covered here (the reference's own controller is called instead, found with
- * dlsym(RTLD_NEXT)): SAM/BAM input, the -ref artifact filter, TDG_REFERENCE_CONTROLLER=1.
+ * dlsym(RTLD_NEXT)): SAM/BAM input, TDG_REFERENCE_CONTROLLER=1.  The -ref artifact filter runs on the GPU
+ * (k_artifact) inside the same streaming job; the reference's get_fasta() reads the sequences.
  *
  * Documented differences, log file only: "Long sequence found. Need to realloc model..." is
  * written once with the number of reads it applies to instead of once per read, and the
@@ -65,7 +66,6 @@ static int needs_reference_controller(struct parameters* param)
 	int i;
 	const char* e = getenv("TDG_REFERENCE_CONTROLLER");
 	if (e && atoi(e)) return 1;
-	if (param->reference_fasta) return 1;
 	for (i = 0; i < param->infiles; i++) {
 		const char* f = param->infile[i];
 		if (ends_with(f, ".sam") || ends_with(f, ".bam") || ends_with(f, ".sam.gz") || ends_with(f, ".bam.gz")) return 1;
@@ -189,6 +189,8 @@ int hmm_controller_multiple(struct parameters* param)
 	}
 	/* ---- the streaming job */
 	{
+		struct fasta* reference_fasta = NULL;
+		int64_t* artifact_counts = NULL;
 		tdg_demux_input* in = calloc(nf, sizeof *in);
 		tdg_demux_job job;
 		tdg_demux_stats st;
@@ -207,7 +209,24 @@ int hmm_controller_multiple(struct parameters* param)
 			in[i].expected_len = file_max_len[i];
 			if (!(rs->num_segments == 1 && rs->type[0] == 'R')) need_gpu = 1;   /* :312 */
 		}
+		/* known contaminants (barcode_hmm.c:208-215): read with the reference's own get_fasta, matched on the device */
+		if (param->reference_fasta) {
+			reference_fasta = get_fasta(reference_fasta, param->reference_fasta);
+			if (!reference_fasta) { status = kslFAIL; free(in); goto DONE; }
+			need_gpu = 1;
+		}
 		if (need_gpu && !(ctx = tdg_shim_context(param))) { status = kslFAIL; free(in); goto DONE; }
+		if (reference_fasta) {
+			job.refset = tdg_shim_get_refset(reference_fasta, param);
+			if (!job.refset) {
+				snprintf(param->errmsg, kslibERRBUFSIZE, "tdg_refset_create: %s", tdg_last_error());
+				status = kslFAIL; free(in); goto DONE;
+			}
+			job.filter_error = param->filter_error;
+			job.ref_chunk_reads = param->num_query;
+			artifact_counts = calloc(reference_fasta->numseq > 0 ? reference_fasta->numseq : 1, sizeof(int64_t));
+			job.artifact_counts = artifact_counts;
+		}
 		for (i = 0; i < nf; i++) {
 			struct read_structure* rs = param->read_structures[i];
 			if (rs->num_segments == 1 && rs->type[0] == 'R') continue;
@@ -271,6 +290,11 @@ int hmm_controller_multiple(struct parameters* param)
 		say(param, "%d	too short\n", (int)st.num_EXTRACT_FAIL_READ_TOO_SHORT);
 		say(param, "%d	low complexity\n", (int)st.num_EXTRACT_FAIL_LOW_COMPLEXITY);
 		say(param, "%d	match artifacts:\n", (int)st.num_EXTRACT_FAIL_MATCHES_ARTIFACTS);
+		if (reference_fasta) {   /* :423-431 */
+			for (i = 0; i < reference_fasta->numseq; i++)
+				if (artifact_counts[i]) say(param, "%d	%s\n", (int)artifact_counts[i], reference_fasta->sn[i]);
+			free(artifact_counts);
+		}
 		if (getenv("TDG_VERBOSE"))
 			fprintf(stderr, "tagdust_b200: %lld reads in %.2f s (busy: line split %.2f s, convert+pack %.2f s, gpu wait %.2f s, write %.2f s)\n",
 			        (long long)st.total_read, st.seconds_total, st.seconds_split, st.seconds_parse, st.seconds_gpu_wait, st.seconds_write);

@@ -196,6 +196,19 @@ static tdg_model* get_model_len(struct model_bag* mb, struct parameters* param, 
 	return out;
 }
 
+/* struct fasta (get_fasta, io.c:1893-1998) -> tdg_refset; one reference file per run, cached by pointer */
+static tdg_refset* g_refset = NULL;
+static const struct fasta* g_refset_src = NULL;
+tdg_refset* tdg_shim_get_refset(struct fasta* f, struct parameters* param)
+{
+	if (ensure_ctx(param) != kslOK) return NULL;
+	if (g_refset && g_refset_src == f) return g_refset;
+	if (g_refset) { tdg_refset_destroy(g_refset); g_refset = NULL; }
+	if (tdg_refset_create(g_ctx, f->string, (const int32_t*)f->s_index, f->numseq, &g_refset) != TDG_OK) return NULL;
+	g_refset_src = f;
+	return g_refset;
+}
+
 tdg_model* tdg_shim_get_model_len(struct model_bag* mb, struct parameters* param, int max_len)
 {
 	return get_model_len(mb, param, max_len);
@@ -309,6 +322,7 @@ static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_
 		int c0, rc = kslOK;
 		if (numseq <= 0) return kslOK;
 		tdg_run_params rq;
+		memset(&rq, 0, sizeof rq);
 		rq.confidence_threshold = param->confidence_threshold; rq.minlen = param->minlen;
 		rq.matchstart = param->matchstart; rq.matchend = param->matchend; rq.dust = 0; rq.want_labels = 0; rq.want_spans = 0;
 		if (ensure_batch(param, numseq < CH ? numseq : CH, order[numseq - 1]->len > 1 ? order[numseq - 1]->len : 1) != kslOK) rc = kslFAIL;
@@ -335,15 +349,22 @@ static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_
 	if (load_batch(param, order, numseq, 1) != kslOK) { if (order != ri) free(order); return kslFAIL; }
 
 	tdg_run_params rp;
+	memset(&rp, 0, sizeof rp);
 	rp.confidence_threshold = param->confidence_threshold;
 	rp.minlen = param->minlen;
 	rp.matchstart = param->matchstart;
 	rp.matchend = param->matchend;
-	/* with -ref the reference order is extract -> match_to_reference -> dust (barcode_hmm.c:2345-2354):
-	 * keep dust on the host then, after the artifact filter */
-	rp.dust = reference_fasta ? 0 : param->dust;
+	/* with -ref the reference's order is extract -> match_to_reference -> dust (barcode_hmm.c:2345-2354); the library
+	 * keeps that order on the device (k_artifact) and reproduces the thread slicing of this call */
+	rp.dust = param->dust;
 	rp.want_labels = (mode == MODE_GET_LABEL);
 	rp.want_spans = 0;
+	if (mode == MODE_GET_LABEL && reference_fasta) {
+		rp.refset = tdg_shim_get_refset(reference_fasta, param);
+		if (!rp.refset) { if (order != ri) free(order); return fail_msg(param, "tdg_refset_create"); }
+		rp.filter_error = param->filter_error;
+		rp.slice_threads = param->num_threads;
+	}
 	tdg_result res;
 	if (tdg_run(g_ctx, m, mode == MODE_GET_LABEL ? TDG_MODE_GET_LABEL : TDG_MODE_GET_PROB, &rp, g_batch, &res) != TDG_OK)
 	{
@@ -373,13 +394,6 @@ static int run_pHMM_impl(struct arch_bag* ab, struct model_bag* mb, struct read_
 			r->len = s_pos;
 		}
 		r->qual[r->len] = 0;                                 /* extract_reads :3308 */
-	}
-	if (mode == MODE_GET_LABEL && reference_fasta) {
-		struct thread_data td;
-		memset(&td, 0, sizeof td);
-		td.ri = ri; td.mb = mb; td.param = param; td.fasta = reference_fasta; td.start = 0; td.end = numseq; td.numseq = numseq;
-		ri = match_to_reference(&td);
-		if (param->dust) ri = dust_sequences(&td);
 	}
 	return kslOK;
 }

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libtagdust_b200.so")
 MODE_GET_LABEL = 1
 MODE_GET_PROB = 4
 MODE_ARCH_COMP = 5
+MODE_RNA_DUST = 6
 EXTRACT_SUCCESS = 0
 EXTRACT_FAIL_ARCHITECTURE_MISMATCH = 1
 EXTRACT_FAIL_READ_TOO_SHORT = 2
@@ -60,6 +61,9 @@ class RunParamsC(C.Structure):
         ("dust", C.c_int32),
         ("want_labels", C.c_int32),
         ("want_spans", C.c_int32),
+        ("refset", C.c_void_p),
+        ("filter_error", C.c_int32),
+        ("slice_threads", C.c_int32),
     ]
 
 
@@ -114,6 +118,8 @@ PROTOTYPES = {
     "tdg_arch_compile": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(ArchParamsC), C.POINTER(C.c_void_p)]),
     "tdg_arch_desc": (C.POINTER(ModelDescC), [C.c_void_p]),
     "tdg_arch_destroy": (None, [C.c_void_p]),
+    "tdg_refset_create": (C.c_int, [C.c_void_p, c_uint8_p, c_int32_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "tdg_refset_destroy": (None, [C.c_void_p]),
     "tdg_batch_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "tdg_batch_destroy": (None, [C.c_void_p]),
     "tdg_batch_clear": (C.c_int, [C.c_void_p]),
@@ -175,6 +181,10 @@ class DemuxJobC(C.Structure):
         ("print_seq_finger", C.c_int32),
         ("threads", C.c_int32),
         ("chunk_reads", C.c_int32),
+        ("refset", C.c_void_p),
+        ("filter_error", C.c_int32),
+        ("ref_chunk_reads", C.c_int32),
+        ("artifact_counts", C.POINTER(C.c_int64)),
     ]
 
 

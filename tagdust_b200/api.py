@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import (MODE_ARCH_COMP, MODE_GET_LABEL, MODE_GET_PROB, ArchParamsC, ModelDesc, ResultC,
+from ._capi import (MODE_ARCH_COMP, MODE_GET_LABEL, MODE_GET_PROB, MODE_RNA_DUST, ArchParamsC, ModelDesc, ResultC,
                     RunParamsC)
 
 
@@ -72,6 +72,23 @@ class Model:
     def close(self):
         if self.h:
             self.ctx.lib.tdg_model_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class RefSet:
+    """tdg_refset: the -ref artifact sequences (struct fasta) on the devices of a context."""
+
+    def __init__(self, ctx, codes, s_index):
+        self.ctx = ctx
+        codes = np.ascontiguousarray(codes, np.uint8)
+        s_index = np.ascontiguousarray(s_index, np.int32)
+        self.h = C.c_void_p()
+        _check(ctx.lib, ctx.lib.tdg_refset_create(ctx.h, codes.ctypes.data_as(_capi.c_uint8_p), s_index.ctypes.data_as(_capi.c_int32_p),
+                                                  len(s_index) - 1, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tdg_refset_destroy(self.h)
             self.h = C.c_void_p()
 
 
@@ -151,15 +168,27 @@ class Context:
         return Batch(self, max_reads, max_len)
 
     @staticmethod
-    def _params(threshold, minlen, matchstart, matchend, dust, want_labels, want_spans=False):
+    def _params(threshold, minlen, matchstart, matchend, dust, want_labels, want_spans=False, refset=None, filter_error=2,
+                slice_threads=1):
         return RunParamsC(float(threshold), int(minlen), int(matchstart), int(matchend), int(dust), int(want_labels),
-                          int(want_spans))
+                          int(want_spans), refset.h if refset is not None else None, int(filter_error), int(slice_threads))
+
+    def refset(self, codes, s_index):
+        return RefSet(self, codes, s_index)
 
     def submit(self, model, batch, mode, *, threshold=0.0, minlen=16, matchstart=-1, matchend=-1, dust=100,
-               want_labels=True, want_spans=False):
-        rp = self._params(threshold, minlen, matchstart, matchend, dust, want_labels, want_spans)
-        _check(self.lib, self.lib.tdg_submit(self.h, model.h, mode, C.byref(rp), batch.h))
-        batch._pending = (mode, bool(want_labels), bool(want_spans))
+               want_labels=True, want_spans=False, refset=None, filter_error=2, slice_threads=1):
+        rp = self._params(threshold, minlen, matchstart, matchend, dust, want_labels, want_spans, refset, filter_error, slice_threads)
+        _check(self.lib, self.lib.tdg_submit(self.h, model.h if model is not None else None, mode, C.byref(rp), batch.h))
+        batch._pending = (mode, bool(want_labels) and mode != MODE_RNA_DUST, bool(want_spans))
+
+    def rna_dust(self, batch, *, dust=100, refset=None, filter_error=2, slice_threads=1):
+        """run_rna_dust() (barcode_hmm.c:2043): reads of a file whose architecture is a single R segment -> read_type."""
+        self.submit(None, batch, MODE_RNA_DUST, dust=dust, want_labels=False, refset=refset, filter_error=filter_error,
+                    slice_threads=slice_threads)
+        res = ResultC()
+        _check(self.lib, self.lib.tdg_wait(batch.h, C.byref(res)))
+        return np.ctypeslib.as_array(res.read_type, shape=(res.n_reads,)).astype(np.int32, copy=True)
 
     def wait(self, batch, copy=True):
         res = ResultC()

@@ -108,6 +108,17 @@ struct KArgs {
 	float confidence_threshold; int32_t minlen; int32_t required_finger_len; int32_t do_extract;
 	int32_t want_labels;
 	int32_t label_smem;        // set by launch_label: the read's labels are staged in shared memory
+	// -ref artifact filter (k_artifact; match_to_reference barcode_hmm.c:2478-2583)
+	const uint8_t* ref_codes;  // device: nuc codes of all reference sequences back to back (fasta->string)
+	const int32_t* ref_index;  // device: [ref_numseq + 1] (fasta->s_index)
+	int32_t ref_numseq;
+	int32_t filter_error;      // param->filter_error
+	int32_t slice_n;           // reads of the whole run_pHMM-equivalent call (the batch)
+	int32_t slice_threads;     // param->num_threads: the reference matches groups of four reads per thread slice
+	int32_t slice_interval;    // (int)((double)slice_n / (double)slice_threads)
+	int32_t slice_base;        // index of this wave's first read inside the batch
+	int32_t model_less;        // run_rna_dust path: no HMM ran, every read starts as EXTRACT_SUCCESS and is kept whole
+	int32_t dust_after;        // param->dust applied by k_artifact (after the artifact match, barcode_hmm.c:2345-2354)
 };
 
 struct LaunchCfg { int ctas; };
@@ -116,6 +127,7 @@ struct LaunchCfg { int ctas; };
 int launch_backward(const KArgs& a, bool store, int ctas, void* stream);
 int launch_forward(const KArgs& a, int ctas, void* stream);
 int launch_label(const KArgs& a, int ctas_decode, void* stream);
+int launch_artifact(const KArgs& a, void* stream);
 int kernels_configure(int smem_bytes); // sets the dynamic shared memory attributes once per device
 size_t decode_smem_bytes(int model_floats, int dyn_cols);
 

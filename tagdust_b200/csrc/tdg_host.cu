@@ -564,6 +564,47 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 }
 
 // ------------------------------------------------------------------------------------------
+// -ref artifact sequences
+// ------------------------------------------------------------------------------------------
+struct tdg_refset {
+	tdg_context* ctx = nullptr;
+	int numseq = 0;
+	std::vector<uint8_t*> d_codes;
+	std::vector<int32_t*> d_index;
+};
+
+extern "C" void tdg_refset_destroy(tdg_refset* r)
+{
+	if (!r) return;
+	for (size_t k = 0; k < r->d_codes.size(); k++) {
+		cudaSetDevice(r->ctx->devs[k].dev);
+		cudaStreamSynchronize(r->ctx->devs[k].compute);
+		cudaFree(r->d_codes[k]); cudaFree(r->d_index[k]);
+	}
+	delete r;
+}
+
+extern "C" int tdg_refset_create(tdg_context* ctx, const uint8_t* codes, const int32_t* s_index, int numseq, tdg_refset** out)
+{
+	if (!ctx || !out || !s_index || numseq < 0 || (numseq > 0 && !codes)) return fail(TDG_EINVAL, "tdg_refset_create: bad argument");
+	*out = nullptr;
+	for (int j = 0; j < numseq; j++)
+		if (s_index[j + 1] < s_index[j]) return fail(TDG_EINVAL, "tdg_refset_create: s_index must be non-decreasing");
+	auto* r = new tdg_refset();
+	r->ctx = ctx; r->numseq = numseq;
+	r->d_codes.assign(ctx->devs.size(), nullptr); r->d_index.assign(ctx->devs.size(), nullptr);
+	std::vector<uint8_t> c(codes, codes + (numseq ? s_index[numseq] : 0));
+	std::vector<int32_t> ix(s_index, s_index + numseq + 1);
+	for (size_t k = 0; k < ctx->devs.size(); k++) {
+		int rc;
+		if (cudaSetDevice(ctx->devs[k].dev) != cudaSuccess) { tdg_refset_destroy(r); return fail(TDG_ECUDA, "cudaSetDevice failed"); }
+		if ((rc = upload(&r->d_codes[k], c)) || (rc = upload(&r->d_index[k], ix))) { tdg_refset_destroy(r); return rc; }
+	}
+	*out = r;
+	return TDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // batches
 // ------------------------------------------------------------------------------------------
 struct Shard {  // one device's part of a batch
@@ -903,7 +944,8 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	KArgs a;
 	fill_model_args(a, m, devk, d);
 	a.store_labels = (p && p->want_labels) ? 1 : 0;
-	const bool want_spans = (mode == TDG_MODE_GET_LABEL && p && p->want_spans && s.spans);
+	const tdg_refset* rs = (mode == TDG_MODE_GET_LABEL && p) ? p->refset : nullptr;
+	const bool want_spans = (mode == TDG_MODE_GET_LABEL && p && (p->want_spans || rs) && s.spans);
 	a.span_stride = want_spans ? b->span_stride : 0;
 	carve_scratch(a, m, d, !bwd_only, wave_ctas);
 	a.words = b->words;
@@ -913,6 +955,13 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 	a.confidence_threshold = p ? p->confidence_threshold : 0.0f;
 	a.minlen = p ? p->minlen : 0;
 	a.dust = (p && mode == TDG_MODE_GET_LABEL) ? p->dust : 0;
+	if (rs) {  // extract -> artifacts -> dust (barcode_hmm.c:2345-2354): dust moves behind the artifact match, into k_artifact
+		a.dust_after = a.dust; a.dust = 0;
+		a.ref_codes = rs->d_codes[devk]; a.ref_index = rs->d_index[devk]; a.ref_numseq = rs->numseq;
+		a.filter_error = p->filter_error;
+		a.slice_n = b->n; a.slice_threads = std::max(1, p->slice_threads);
+		a.slice_interval = (int)((double)b->n / (double)a.slice_threads);
+	}
 	a.do_extract = (mode == TDG_MODE_GET_LABEL);
 	a.want_labels = want_labels;
 	const int wave = wave_ctas * kBlock;
@@ -958,6 +1007,11 @@ static int queue_decode(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_
 				prof_mark(d, 2, stream);
 				if ((e = launch_label(a, ctas, stream))) { fail(TDG_ECUDA, "k_label launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
 				prof_mark(d, 2, stream);
+				launches++;
+			}
+			if (rs) {
+				a.slice_base = s.first + w0;
+				if ((e = launch_artifact(a, stream))) { fail(TDG_ECUDA, "k_artifact launch: %s", cudaGetErrorString((cudaError_t)e)); return -1; }
 				launches++;
 			}
 		}
@@ -1074,12 +1128,53 @@ static void fill_result(tdg_batch* b, tdg_result* out)
 	out->spans = b->want_spans ? b->h_spans : nullptr;
 }
 
+// run_rna_dust (barcode_hmm.c:2043) for a batch of reads without a model: artifact filter + dust in one kernel
+static int submit_rna_dust(tdg_context* ctx, const tdg_run_params* p, tdg_batch* b)
+{
+	if (!p || !b) return fail(TDG_EINVAL, "run params and batch required");
+	if (b->ctx != ctx) return fail(TDG_EINVAL, "batch belongs to another context");
+	if (p->refset && p->refset->ctx != ctx) return fail(TDG_EINVAL, "refset belongs to another context");
+	if (b->pending) return fail(TDG_EINVAL, "batch already submitted; call tdg_wait first");
+	assign_shards(b);
+	for (size_t k = 0; k < ctx->devs.size(); k++) {
+		DeviceCtx& d = ctx->devs[k];
+		Shard& s = b->shard[k];
+		if (s.n == 0) continue;
+		CK(cudaSetDevice(d.dev));
+		int rc;
+		if ((rc = upload_shard(b, (int)k, s.copy))) return rc;
+		CK(cudaEventRecord(s.h2d_done, s.copy));
+		CK(cudaStreamWaitEvent(d.compute, s.h2d_done, 0));
+		KArgs a;
+		memset(&a, 0, sizeof a);
+		a.n_reads = s.n; a.words = b->words; a.seq = s.seq; a.len = s.len; a.read_type = s.read_type;
+		a.model_less = 1; a.dust_after = p->dust;
+		if (p->refset) {
+			a.ref_codes = p->refset->d_codes[k]; a.ref_index = p->refset->d_index[k]; a.ref_numseq = p->refset->numseq;
+			a.filter_error = p->filter_error;
+		}
+		a.slice_n = b->n; a.slice_threads = std::max(1, p->slice_threads);
+		a.slice_interval = (int)((double)b->n / (double)a.slice_threads);
+		a.slice_base = s.first;
+		const int e = launch_artifact(a, d.compute);
+		if (e) return fail(TDG_ECUDA, "k_artifact launch: %s", cudaGetErrorString((cudaError_t)e));
+		CK(cudaEventRecord(s.k_done, d.compute));
+		CK(cudaStreamWaitEvent(s.copy, s.k_done, 0));
+		CK(cudaMemcpyAsync(b->h_read_type + s.first, s.read_type, (size_t)s.n * 4, cudaMemcpyDeviceToHost, s.copy));
+		CK(cudaEventRecord(s.d2h_done, s.copy));
+	}
+	b->pending = true; b->pending_mode = TDG_MODE_RNA_DUST; b->want_labels = false; b->want_spans = false;
+	return TDG_OK;
+}
+
 extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_run_params* p, tdg_batch* b)
 {
 	if (!ctx) return fail(TDG_EINVAL, "NULL context");
+	if (mode == TDG_MODE_RNA_DUST) return submit_rna_dust(ctx, p, b);
 	if (mode != TDG_MODE_GET_LABEL && mode != TDG_MODE_GET_PROB && mode != TDG_MODE_ARCH_COMP)
 		return fail(TDG_EINVAL, "unsupported mode %d (MODE_TRAIN has no live caller in the reference)", mode);
 	if (mode != TDG_MODE_ARCH_COMP && !p) return fail(TDG_EINVAL, "run params required");
+	if (p && p->refset && p->refset->ctx != ctx) return fail(TDG_EINVAL, "refset belongs to another context");
 	std::lock_guard<std::mutex> model_lock(g_model_mu);
 	int rc = check_compat(m, b, p);
 	if (rc) return rc;
@@ -1089,7 +1184,7 @@ extern "C" int tdg_submit(tdg_context* ctx, tdg_model* m, int mode, const tdg_ru
 	const bool want_labels = mode != TDG_MODE_ARCH_COMP && p->want_labels;   // label rows come back to the host
 	const bool want_spans = mode == TDG_MODE_GET_LABEL && p->want_spans;
 	if (run_dp && (rc = ensure_label_buffers(b, want_labels))) return rc;
-	if (want_spans && (rc = ensure_span_buffers(b, span_stride_of(m)))) return rc;
+	if ((want_spans || (mode == TDG_MODE_GET_LABEL && p->refset)) && (rc = ensure_span_buffers(b, span_stride_of(m)))) return rc;
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
 		DeviceCtx& d = ctx->devs[k];
 		Shard& s = b->shard[k];

@@ -1224,6 +1224,165 @@ __global__ void __launch_bounds__(kDpBlock) k_label(const KArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// k_artifact: the -ref artifact filter, match_to_reference (barcode_hmm.c:2478-2583), then dust_sequences
+// (:2407-2467) in the reference's order extract -> artifacts -> dust (:2345-2354).  Thread-per-read.
+//
+// The pattern is the read as make_extracted_read left it (spacer 65 outside the R-run spans), matched on both strands
+// against every reference sequence with Myers' bit-vector algorithm in 64-bit words.  The reference has two variants and
+// which one a read gets depends on its place in the thread slice of the run_pHMM call: reads in the groups of four at
+// the start of a slice take the best match of validate_bpm_sse -> bmp_single (misc.c:718-765: first min(len, 63)
+// pattern characters); the last (slice length mod 4) reads take the first reference sequence that bpm_check_error
+// (misc.c:572-636: bits at index mod 64, score read at bit min(#bases, 31) - 1, score starting at len) puts within the
+// cut-off.  Both are reproduced as they are.  Reference characters are staged through shared memory in tiles that all
+// reads of the CTA walk together; both strands advance in the same loop (two independent dependency chains).
+// ------------------------------------------------------------------------------------------
+constexpr int kArtBlock = 128;
+constexpr int kArtTile = 2048;
+
+struct Myers {
+	uint64_t VP, VN;
+	__device__ __forceinline__ void step(uint64_t eq, uint64_t& HP, uint64_t& HN)
+	{
+		const uint64_t X = eq | VN;
+		const uint64_t D0 = ((VP + (X & VP)) ^ VP) | X;
+		HN = VP & D0;
+		HP = VN | ~(VP | D0);
+		const uint64_t Y = HP << 1;
+		VN = Y & D0;
+		VP = (HN << 1) | ~(Y | D0);
+	}
+};
+
+__global__ void __launch_bounds__(kArtBlock) k_artifact(const KArgs a)
+{
+	__shared__ uint8_t s_t[kArtTile];
+	const int read = blockIdx.x * kArtBlock + threadIdx.x;
+	const bool valid = read < a.n_reads;
+	const int rlen = valid ? a.len[read] : 0;
+	int rt = 0;
+	bool extracted = false;
+	if (valid && !a.model_less) { rt = a.read_type[read]; extracted = a.extracted[read] != 0; }
+	const SeqReader rd = make_reader(a, valid ? read : 0);
+	const uint16_t* sp = (a.spans && valid) ? a.spans + (size_t)read * a.span_stride * 2 : nullptr;
+	// residue j of the rewritten read
+	auto e = [&](int j) -> int {
+		if (j >= rlen) return 0;
+		if (extracted) {
+			bool in = false;
+			for (int k = 0; k < a.span_stride; ++k) {
+				const int s0 = sp[2 * k], sl = sp[2 * k + 1];
+				if (sl == 0) break;
+				if (j >= s0 && j < s0 + sl) { in = true; break; }
+			}
+			if (!in) return 65;
+		}
+		return rd.code(j);
+	};
+	auto rc_of = [](int c) -> int { return c == 65 ? 65 : (c < 4 ? 3 - c : 4); };   // rev_nuc_code, nuc_code.c:68-72
+
+	bool active = valid && rt == 0 && a.ref_numseq > 0;   // only EXTRACT_SUCCESS reads can become artifacts (:2546, :2576)
+	// place in the reference's thread slice (run_pHMM :1911-1922 / run_rna_dust :2063-2072)
+	bool grouped = true;
+	if (active) {
+		const int gi = a.slice_base + read, T = a.slice_threads, iv = a.slice_interval;
+		int t = iv > 0 ? gi / iv : T - 1;
+		if (t > T - 1) t = T - 1;
+		const int start = t * iv, end = (t == T - 1) ? a.slice_n : start + iv;
+		grouped = (gi - start) < ((end - start) / 4) * 4;
+	}
+	// pattern bit-vectors, forward and reverse-complement strand
+	uint64_t Bf[4] = {0, 0, 0, 0}, Br[4] = {0, 0, 0, 0};
+	int m = 0, sh = 0;
+	uint64_t mask = 0;
+	if (active) {
+		if (grouped) {
+			m = rlen > 63 ? 63 : rlen;
+			for (int i = 0; i < m; ++i) {
+				const int c = e(i);
+				if (c != 65) Bf[c & 3] |= (uint64_t)1 << i;
+				const int r = rc_of(e(rlen - 1 - i));
+				if (r != 65) Br[r & 3] |= (uint64_t)1 << i;
+			}
+			mask = m > 0 ? (uint64_t)1 << (m - 1) : 0;
+		} else {
+			int nf = 0;   // the number of bases is the same on both strands
+			for (int i = 0; i < rlen; ++i) {
+				const int c = e(i);
+				if (c != 65) { Bf[c & 3] |= (uint64_t)1 << (i & 63); nf++; }
+				const int r = rc_of(e(rlen - 1 - i));
+				if (r != 65) Br[r & 3] |= (uint64_t)1 << (i & 63);
+			}
+			m = nf > 31 ? 31 : nf;
+			sh = (m - 1) & 63;
+			mask = (uint64_t)1 << sh;
+		}
+	}
+	int best = 100000, best_id = 0, hit = 0;
+	for (int j = 0; j < a.ref_numseq; ++j) {
+		const int t0 = a.ref_index[j], n = a.ref_index[j + 1] - t0;
+		Myers F, R;
+		long long df, dr;   // running scores
+		int kf, kr;
+		if (grouped) { F.VP = R.VP = m > 0 ? (((uint64_t)1 << m) - 1) : 0; df = dr = m; kf = kr = m; }
+		else { F.VP = R.VP = ~(uint64_t)0; df = dr = rlen; kf = kr = m; }
+		F.VN = R.VN = 0;
+		const bool run = active && !hit && (grouped ? rlen > 0 : true);
+		for (int base = 0; base < n; base += kArtTile) {
+			const int cnt = min(kArtTile, n - base);
+			__syncthreads();
+			for (int k = threadIdx.x; k < cnt; k += kArtBlock) s_t[k] = a.ref_codes[t0 + base + k] & 3;
+			__syncthreads();
+			if (!run) continue;
+			for (int i = 0; i < cnt; ++i) {
+				const int c = s_t[i];
+				uint64_t HP, HN;
+				F.step(Bf[c], HP, HN);
+				if (grouped) { df += (HP & mask) ? 1 : 0; df -= (HN & mask) ? 1 : 0; if (df < kf) kf = (int)df; }
+				else { df += (long long)((HP & mask) >> sh); df -= (long long)((HN & mask) >> sh); if ((unsigned long long)df < (unsigned long long)kf) kf = (int)df; }
+				R.step(Br[c], HP, HN);
+				if (grouped) { dr += (HP & mask) ? 1 : 0; dr -= (HN & mask) ? 1 : 0; if (dr < kr) kr = (int)dr; }
+				else { dr += (long long)((HP & mask) >> sh); dr -= (long long)((HN & mask) >> sh); if ((unsigned long long)dr < (unsigned long long)kr) kr = (int)dr; }
+			}
+		}
+		if (!active || hit) continue;
+		if (grouped) {
+			const int ef = rlen > 0 ? kf : n, er = rlen > 0 ? kr : n;   // validate_bpm_sse: an empty query scores n
+			if (ef < best) { best = ef; best_id = j + 1; }
+			if (er < best) { best = er; best_id = j + 1; }
+		} else {
+			if (kf <= a.filter_error || kr <= a.filter_error) hit = j + 1;   // forward is tried first, the id is the same
+		}
+	}
+	if (!valid) return;
+	if (active) {
+		if (grouped && best <= a.filter_error) hit = best_id;
+		if (hit) rt = (hit << 8) | 5;   // EXTRACT_FAIL_MATCHES_ARTIFACTS, io.h:36-52
+	}
+	if (a.dust_after) {   // dust_sequences (:2407-2467), same arithmetic as the tail of k_label
+		uint8_t cnt[64];
+		for (int j = 0; j < 64; ++j) cnt[j] = 0;
+		int c = 0;
+		while (e(c) == 65) c++;
+		unsigned key = ((e(c) & 0x3) << 2) | (e(c + 1) & 0x3);
+		int dl = rlen; if (dl > 64) dl = 64;
+		c += 2;
+		for (int j = c; j < dl; ++j) {
+			const int v = e(j);
+			if (v == 65) break;
+			key = (key << 2) | (v & 0x3);
+			cnt[key & 0x3F]++;
+			c++;
+		}
+		int si = 0;
+		for (int j = 0; j < 64; ++j) si += (int)cnt[j] * ((int)cnt[j] - 1) / 2;
+		double s = (double)si;
+		s = s / (double)(c - 3) * 10.0;
+		if (s > (double)a.dust_after) rt = 6;
+	}
+	a.read_type[read] = rt;
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 size_t decode_smem_bytes(int model_floats, int dyn_cols)
@@ -1285,6 +1444,14 @@ int launch_label(const KArgs& a, int ctas_decode, void* stream)
 	if (b.label_smem) smem += lab_bytes;
 	const int ctas = (threads + bs - 1) / bs;
 	k_label<<<ctas, bs, smem, (cudaStream_t)stream>>>(b);
+	return (int)cudaGetLastError();
+}
+
+int launch_artifact(const KArgs& a, void* stream)
+{
+	const int ctas = (a.n_reads + kArtBlock - 1) / kArtBlock;
+	if (ctas == 0) return 0;
+	k_artifact<<<ctas, kArtBlock, 0, (cudaStream_t)stream>>>(a);
 	return (int)cudaGetLastError();
 }
 

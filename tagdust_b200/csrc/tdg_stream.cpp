@@ -782,7 +782,10 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	const int threads = std::max(1, job->threads);
 	// default chunk: two waves per device of the context (a chunk is sharded contiguously over the devices)
 	const int ndev = ctx ? std::max(1, tdg_device_count(ctx)) : 1;
-	const int chunk_reads = job->chunk_reads > 0 ? job->chunk_reads : 2 * 148 * 512 * ndev;
+	// with -ref a chunk is one chunk of the reference's own loop: its thread slices decide how each read is matched
+	const int chunk_reads = job->refset ? (job->ref_chunk_reads > 0 ? job->ref_chunk_reads : 1000001)
+	                                    : (job->chunk_reads > 0 ? job->chunk_reads : 2 * 148 * 512 * ndev);
+	if (job->refset && !ctx) return failf(TDG_EINVAL, "tdg_demux_run: a GPU context is required for the artifact filter");
 	const int nalt = job->num_alternatives;
 	if (nalt < 2) return failf(TDG_EINVAL, "num_alternatives must be >= 2");
 	const double t_start = now_s();
@@ -841,30 +844,42 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	Queue<int> q_free, q_conv, q_gpu, q_write;
 	for (int k = 0; k < NSLOT; k++) q_free.push(k);
 	Shared sh;
-	// pinned staging is slow to create: make all slots' batches at once, on their own threads, while
-	// the first chunk is being split (a longer read later on re-creates the batch of that slot)
+	// Pinned staging is slow to create (page pinning runs at ~1 GB/s and is serialised per process), so the slots' batches
+	// are made one after the other on a set-up thread and every slot is released to the pipeline as soon as its own batch
+	// exists: chunk 0 is on the GPU while the staging of slots 1 and 2 is still being pinned.  (A longer read later on
+	// re-creates the batch of that slot.)  The scratch arenas (tens of GB per device) are allocated meanwhile.
 	std::vector<std::thread> t_alloc;
-	for (int k = 0; k < NSLOT; k++)
-		for (int i = 0; i < NI; i++)
-			if (job->inputs[i].model && (job->inputs[i].expected_len > 0 || job->inputs[i].max_seq_len > 0))
-				t_alloc.emplace_back([&, k, i] {
-					const double ta = now_s();
-					Slot& s = slots[k];
-					s.batch_reads[i] = std::min(chunk_reads, 1 << 24);
-					s.batch_len[i] = job->inputs[i].expected_len > 0 ? job->inputs[i].expected_len : job->inputs[i].max_seq_len;
-					// the label rows stay on the device (the writer works from the R-run spans): no pinned label staging
-					if (tdg::batch_acquire(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK ||
-					    tdg::batch_prepare(s.batch[i], job->inputs[i].model, false) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
-					if (getenv("TDG_TRACE")) fprintf(stderr, "[trace] batch for slot %d input %d created in %.3f s\n", k, i, now_s() - ta);
-				});
-	// the scratch arenas (tens of GB per device) are allocated meanwhile, one thread per device
-	for (int i = 0; i < NI; i++)
-		if (job->inputs[i].model)
-			t_alloc.emplace_back([&, i] {
+	std::mutex ready_mu;
+	std::condition_variable ready_cv;
+	std::vector<char> slot_ready((size_t)NSLOT, 0);
+	bool scratch_ready = false;
+	t_alloc.emplace_back([&] {
+		for (int k = 0; k < NSLOT; k++) {
+			for (int i = 0; i < NI && !sh.failed; i++) {
+				if (!((job->inputs[i].model || job->refset) && (job->inputs[i].expected_len > 0 || job->inputs[i].max_seq_len > 0))) continue;
+				const double ta = now_s();
+				Slot& s = slots[k];
+				s.batch_reads[i] = std::min(chunk_reads, 1 << 24);
+				s.batch_len[i] = job->inputs[i].expected_len > 0 ? job->inputs[i].expected_len : job->inputs[i].max_seq_len;
+				// the label rows stay on the device (the writer works from the R-run spans): no pinned label staging
+				if (tdg::batch_acquire(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK ||
+				    (job->inputs[i].model && tdg::batch_prepare(s.batch[i], job->inputs[i].model, false) != TDG_OK)) sh.fail(TDG_ECUDA, tdg_last_error());
+				if (getenv("TDG_TRACE")) fprintf(stderr, "[trace] batch for slot %d input %d created in %.3f s\n", k, i, now_s() - ta);
+			}
+			{ std::lock_guard<std::mutex> l(ready_mu); slot_ready[k] = 1; }
+			ready_cv.notify_all();
+		}
+	});
+	t_alloc.emplace_back([&] {
+		for (int i = 0; i < NI && !sh.failed; i++)
+			if (job->inputs[i].model) {
 				const double ta = now_s();
 				if (tdg::scratch_prepare(ctx, job->inputs[i].model) != TDG_OK) sh.fail(TDG_ECUDA, tdg_last_error());
 				if (getenv("TDG_TRACE")) fprintf(stderr, "[trace] scratch for input %d ready in %.3f s\n", i, now_s() - ta);
-			});
+			}
+		{ std::lock_guard<std::mutex> l(ready_mu); scratch_ready = true; }
+		ready_cv.notify_all();
+	});
 	const bool trace = getenv("TDG_TRACE") != nullptr && getenv("TDG_TRACE")[0] != 0;
 	auto tr = [&](const char* stage, int k, double t0) {
 		if (trace) fprintf(stderr, "[trace] %-8s chunk-slot %d  %.3f -> %.3f s\n", stage, k, t0 - t_start, now_s() - t_start);
@@ -905,7 +920,6 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 
 	// ---- stage 1b: conversion + packing on the worker pool
 	std::thread t_parse([&] {
-		for (auto& t : t_alloc) t.join();
 		try {
 		std::vector<int> run_max(NI);
 		for (int i = 0; i < NI; i++) run_max[i] = job->inputs[i].max_seq_len;
@@ -913,6 +927,8 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			int k;
 			if (!q_conv.pop(k) || sh.failed) break;
 			Slot& s = slots[k];
+			{ std::unique_lock<std::mutex> l(ready_mu); ready_cv.wait(l, [&] { return slot_ready[k] != 0; }); }
+			if (sh.failed) break;
 			const double t0 = now_s();
 			bool ok = true;
 			if (!s.last) {
@@ -927,10 +943,10 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					run_max[i] = mx;
 					long_events += ev;
 					tdg_model* m = job->inputs[i].model;
-					if (!m) continue;
+					if (!m && !job->refset) continue;   // model-less files reach the GPU only for the artifact filter
 					int need = pc.max_len;
 					if (job->matchstart != -1 || job->matchend != -1) need = std::max(need, job->matchend);
-					if (need > tdg_model_max_len(m)) tdg_model_set_max_len(m, need + 10);
+					if (m && need > tdg_model_max_len(m)) tdg_model_set_max_len(m, need + 10);
 					if (!s.batch[i] || s.batch_reads[i] < pc.n || s.batch_len[i] < pc.max_len) {
 						if (s.batch[i]) tdg_batch_destroy(s.batch[i]);
 						s.batch[i] = nullptr;
@@ -961,7 +977,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			Slot& s = slots[k];
 			const double t0 = now_s();
 			for (int i = 0; i < NI; i++)
-				if (job->inputs[i].model && !s.last)
+				if ((job->inputs[i].model || job->refset) && !s.last)
 					if (tdg_wait(s.batch[i], &s.res[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); return false; }
 			sec_gpu += now_s() - t0;
 			tr("gpu-wait", k, t0);
@@ -972,18 +988,23 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			int k;
 			if (!q_gpu.pop(k)) break;
 			if (sh.failed) break;
+			{ std::unique_lock<std::mutex> l(ready_mu); ready_cv.wait(l, [&] { return scratch_ready; }); }
+			if (sh.failed) break;
 			Slot& s = slots[k];
 			bool ok = true;
 			const double ts = now_s();
 			if (!s.last)
 				for (int i = 0; i < NI && ok; i++) {
 					tdg_model* m = job->inputs[i].model;
-					if (!m) continue;
+					if (!m && !job->refset) continue;
 					tdg_run_params rp;
+					memset(&rp, 0, sizeof rp);
 					rp.confidence_threshold = job->inputs[i].confidence_threshold;
 					rp.minlen = job->minlen; rp.matchstart = job->matchstart; rp.matchend = job->matchend;
 					rp.dust = job->dust; rp.want_labels = 0; rp.want_spans = 1;
-					if (tdg_submit(ctx, m, TDG_MODE_GET_LABEL, &rp, s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; }
+					rp.refset = job->refset; rp.filter_error = job->filter_error; rp.slice_threads = threads;
+					// a file whose architecture is a single R segment: run_rna_dust (artifact filter + dust), no HMM
+					if (tdg_submit(ctx, m, m ? TDG_MODE_GET_LABEL : TDG_MODE_RNA_DUST, &rp, s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; }
 				}
 			if (!ok) break;
 			tr("submit", k, ts);
@@ -1027,6 +1048,8 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 							rt[i] = R.read_type[r]; fpv[i] = R.fingerprint[r]; mq[i] = R.mapq[r];
 							if (i == job->barcode_input) barcode = R.barcode[r];
 							if (R.extracted[r]) { spv[i] = R.spans + r * (size_t)R.span_stride * 2; spn[i] = R.span_stride; }
+						} else if (job->refset) {
+							rt[i] = s.res[i].read_type[r]; fpv[i] = -1; mq[i] = -1.0f;  // run_rna_dust on the device (artifact filter, dust)
 						} else {
 							rt[i] = TDG_EXTRACT_SUCCESS; fpv[i] = -1; mq[i] = -1.0f;  // do_rna_dust + clear_read_info (io.c:2063-2093)
 							if (job->dust && dust_low_complexity(pc.codes.data() + pc.seq_off[r], pc.len[r], job->dust)) rt[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
@@ -1040,7 +1063,10 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 						case TDG_EXTRACT_FAIL_ARCHITECTURE_MISMATCH: tl[4]++; break;
 						case TDG_EXTRACT_FAIL_MATCHES_ARTIFACTS: tl[5]++; tl[6]++; break;  // falls through in the reference
 						case TDG_EXTRACT_FAIL_LOW_COMPLEXITY: tl[6]++; break;
-						default: tl[5]++; break;
+						default:  // (sequence number << 8) | EXTRACT_FAIL_MATCHES_ARTIFACTS: counted per reference sequence (:379-382)
+							tl[5]++;
+							if (job->artifact_counts && (merged >> 8) >= 1) __atomic_fetch_add(&job->artifact_counts[(merged >> 8) - 1], (int64_t)1, __ATOMIC_RELAXED);
+							break;
 					}
 					const int sel = (merged == TDG_EXTRACT_SUCCESS) ? (barcode != -1 ? (barcode & 0xFF) : 0) : nalt - 1;
 					for (int i = 0; i < NI; i++) {
@@ -1135,6 +1161,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	});
 
 	t_split.join();
+	for (auto& t : t_alloc) t.join();
 	if (sh.failed) { q_conv.close(); q_free.close(); }
 	t_parse.join();
 	if (sh.failed) { q_gpu.close(); q_free.close(); }

@@ -25,7 +25,22 @@ def init(backend=None):
         if backend == "nccl":
             kw["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend, **kw)
+        global _cpu_group
+        # a host-side group: a rank that waits in an NCCL barrier keeps a spinning kernel resident on ITS GPU, which
+        # would take SMs away from a rank that drives all GPUs of the box from one process (bench.py's strong-scaling leg)
+        _cpu_group = dist.new_group(backend="gloo") if backend != "gloo" else None
     return rank, world, local
+
+
+_cpu_group = None
+
+
+def cpu_barrier():
+    """Barrier that waits on the host only (gloo): the GPUs of the waiting ranks stay idle."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier(group=_cpu_group) if _cpu_group is not None else dist.barrier()
 
 
 def _dev():

@@ -48,7 +48,8 @@ def format_rq(v):
 
 
 def demux_run(ctx, inputs, outfile, *, barcode_input=-1, barcode_names=None, minlen=16, dust=100, matchstart=-1,
-              matchend=-1, print_seq_finger=0, threads=8, chunk_reads=0):
+              matchend=-1, print_seq_finger=0, threads=8, chunk_reads=0, refset=None, filter_error=2, ref_chunk_reads=0,
+              artifact_counts=None):
     """inputs: list of dict(path, model (api.Model or None), num_read_segments, threshold, max_seq_len, fasta=-1).
     barcode_names: sequences of the first B segment without the trailing N alternative."""
     lib = _capi.load_library()
@@ -75,6 +76,11 @@ def demux_run(ctx, inputs, outfile, *, barcode_input=-1, barcode_names=None, min
     job.outfile = str(outfile).encode()
     job.minlen, job.dust, job.matchstart, job.matchend = minlen, dust, matchstart, matchend
     job.print_seq_finger, job.threads, job.chunk_reads = print_seq_finger, threads, chunk_reads
+    if refset is not None:
+        job.refset = refset.h
+        job.filter_error, job.ref_chunk_reads = filter_error, ref_chunk_reads
+        if artifact_counts is not None:   # int64 numpy array, one counter per reference sequence
+            job.artifact_counts = artifact_counts.ctypes.data_as(C.POINTER(C.c_int64))
     st = _capi.DemuxStatsC()
     _check(lib, lib.tdg_demux_run(ctx.h if ctx is not None else None, C.byref(job), C.byref(st)))
     return {k: getattr(st, k) for k, _ in st._fields_}

@@ -180,6 +180,42 @@ class RefHarness:
         assert st == 0
         return out
 
+    # -- -ref artifact filter (match_to_reference, barcode_hmm.c:2478-2583)
+    def set_reference(self, param, ref_codes, s_index, filter_error=2):
+        """ref_codes: uint8 nuc codes of all reference sequences back to back; s_index[numseq+1]; empty = remove."""
+        self.L.refh_set_reference.argtypes = [C.c_void_p, u8p, i32p, C.c_int, C.c_int]
+        rc = np.ascontiguousarray(ref_codes, np.uint8)
+        si = np.ascontiguousarray(s_index, np.int32)
+        self.L.refh_set_reference(param, _p(rc, u8p), _p(si, i32p), len(si) - 1 if len(si) else 0, filter_error)
+
+    def run_phmm_ref(self, mb, param, codes, lens):
+        self.L.refh_run_phmm_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_int, u8p, C.c_int, i32p, f32p, i32p, i32p, i32p, u8p]
+        codes = np.ascontiguousarray(codes, np.uint8)
+        lens = np.ascontiguousarray(lens, np.int32)
+        n, stride = codes.shape
+        out = dict(mapq=np.zeros(n, np.float32), read_type=np.zeros(n, np.int32), barcode=np.zeros(n, np.int32),
+                   fingerprint=np.zeros(n, np.int32), seq=np.zeros((n, stride), np.uint8))
+        st = self.L.refh_run_phmm_ref(mb, param, n, _p(codes, u8p), stride, _p(lens, i32p), _p(out["mapq"], f32p),
+                                      _p(out["read_type"], i32p), _p(out["barcode"], i32p), _p(out["fingerprint"], i32p),
+                                      _p(out["seq"], u8p))
+        assert st == 0
+        return out
+
+    def run_rna_dust(self, param, codes, lens):
+        self.L.refh_run_rna_dust.argtypes = [C.c_void_p, C.c_int, u8p, C.c_int, i32p, i32p]
+        codes = np.ascontiguousarray(codes, np.uint8)
+        lens = np.ascontiguousarray(lens, np.int32)
+        n, stride = codes.shape
+        rt = np.zeros(n, np.int32)
+        assert self.L.refh_run_rna_dust(param, n, _p(codes, u8p), stride, _p(lens, i32p), _p(rt, i32p)) == 0
+        return rt
+
+    def myers(self, which, t, p):
+        fn = self.L.refh_bmp_single if which == "bmp_single" else self.L.refh_bpm_check_error
+        fn.argtypes = [u8p, u8p, C.c_int, C.c_int]
+        t = np.ascontiguousarray(t, np.uint8); p = np.ascontiguousarray(p, np.uint8)
+        return fn(_p(t, u8p), _p(p, u8p), len(t), len(p))
+
     def run_arch_comp(self, mbs, param, codes, lens):
         codes = np.ascontiguousarray(codes, np.uint8)
         lens = np.ascontiguousarray(lens, np.int32)
@@ -243,6 +279,26 @@ class Oracle:
                             _p(out["seq"], u8p), _p(out["len"], i32p))
         assert st == 0
         return out
+
+    def set_reference(self, ref_codes, s_index, filter_error=2):
+        self.L.orc_set_reference.argtypes = [u8p, i32p, C.c_int, C.c_int]
+        self._ref = (np.ascontiguousarray(ref_codes, np.uint8), np.ascontiguousarray(s_index, np.int32))   # keep alive
+        self.L.orc_set_reference(_p(self._ref[0], u8p), _p(self._ref[1], i32p), max(len(self._ref[1]) - 1, 0), filter_error)
+
+    def run_rna_dust(self, codes, lens, dust=100, threads=1):
+        self.L.orc_run_rna_dust.argtypes = [C.c_int, u8p, C.c_size_t, i32p, C.c_int, C.c_int, i32p]
+        codes = np.ascontiguousarray(codes, np.uint8)
+        lens = np.ascontiguousarray(lens, np.int32)
+        n, stride = codes.shape
+        rt = np.zeros(n, np.int32)
+        assert self.L.orc_run_rna_dust(n, _p(codes, u8p), stride, _p(lens, i32p), threads, dust, _p(rt, i32p)) == 0
+        return rt
+
+    def myers(self, which, t, p):
+        fn = self.L.orc_bmp_single if which == "bmp_single" else self.L.orc_bpm_check_error
+        fn.argtypes = [u8p, u8p, C.c_int, C.c_int]
+        t = np.ascontiguousarray(t, np.uint8); p = np.ascontiguousarray(p, np.uint8)
+        return fn(_p(t, u8p), _p(p, u8p), len(t), len(p))
 
     def arch_compare(self, descs, codes, lens, threads=1):
         codes = np.ascontiguousarray(codes, np.uint8)

@@ -165,6 +165,59 @@ def test_architecture_selection_from_arch_file(tmp_path):
     assert "F:NNNN" in log and "Confidence" in log
 
 
+def write_reference_fasta(path, fq_files, rng, n_from_reads=30):
+    """Contaminant sequences: windows of some reads (either strand, some with an edit) plus random ones."""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    seqs = []
+    for fq in fq_files:
+        lines = open(fq).read().splitlines()
+        reads = lines[1::4]
+        for k in range(n_from_reads):
+            s = reads[int(rng.integers(0, len(reads)))][:90]
+            if k % 2:
+                s = "".join(comp[c] for c in reversed(s))
+            if k % 3 == 0:
+                s = s[:20] + "ACGT"[int(rng.integers(0, 4))] + s[21:]
+            pad = "".join(rng.choice(list("ACGT"), size=int(rng.integers(0, 25))))
+            seqs.append(pad + s + pad[::-1])
+    for _ in range(6):
+        seqs.append("".join(rng.choice(list("ACGT"), size=int(rng.integers(30, 400)))))
+    with open(path, "w") as fh:
+        for k, s in enumerate(seqs):
+            fh.write(f">contaminant_{k} some description\n")
+            for i in range(0, len(s), 60):
+                fh.write(s[i:i + 60] + "\n")
+
+
+@pytest.mark.parametrize("threads", [1, 4, 3])
+def test_ref_artifact_filter_cli(tmp_path, threads):
+    """-ref: reads within -fe edits of a known contaminant (either strand) go to the `un` file and are counted per
+    contaminant in the log.  The read comes first in the architecture and is longer than 63 nt (with 5' segments the
+    rewritten read starts with spacers, which the reference's filter can never match).  The second file is a plain
+    R:N read (run_rna_dust path).  The reference matches per thread slice (groups of four / the rest), so -t matters."""
+    tmp = str(tmp_path)
+    rng = np.random.default_rng(41)
+    make_fastq(os.path.join(tmp, "r1.fq"), 2300, [("R", None), ("B", TAGS)], seed=31, read_len=(70, 90), short=False)
+    make_fastq(os.path.join(tmp, "r2.fq"), 2300, [("R", None)], seed=32, read_len=(50, 80), short=False, name_fmt="M1:7:FC:1:{t}:{x}:{y} 2:N:0:1")
+    write_reference_fasta(os.path.join(tmp, "contaminants.fa"), [os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")], rng)
+    outs = {}
+    for tag, binary in (("cpu", os.path.join(REF, "tagdust_rtest")), ("gpu", GPU_BIN)):
+        d = os.path.join(tmp, tag)
+        os.makedirs(d, exist_ok=True)
+        r = subprocess.run(f"{binary} -seed 42 -t {threads} -ref contaminants.fa -fe 2 -1 R:N -2 {BARC} r1.fq r2.fq -o {d}/out", cwd=tmp, shell=True,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, f"{tag}: {r.stdout}\n{r.stderr}"
+        outs[tag] = d
+    a = sorted(glob.glob(os.path.join(outs["cpu"], "out*.fq")))
+    b = sorted(glob.glob(os.path.join(outs["gpu"], "out*.fq")))
+    assert [os.path.basename(x) for x in a] == [os.path.basename(x) for x in b] and a
+    for x, y in zip(a, b):
+        assert filecmp.cmp(x, y, shallow=False), f"{os.path.basename(x)} differs"
+    cpu_log, gpu_log = summary_lines(f"{outs['cpu']}/out_logfile.txt"), summary_lines(f"{outs['gpu']}/out_logfile.txt")
+    assert cpu_log == gpu_log
+    assert any("contaminant_" in line for line in gpu_log), "no artifact was counted: the test set is too easy"
+
+
 def test_streaming_on_two_devices_matches_one(tmp_path):
     """tdg_demux_run over a 2-GPU context (every chunk sharded contiguously over the devices) writes the
     same bytes as over one GPU."""
