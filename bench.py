@@ -169,6 +169,155 @@ def files_e2e(ctx, model, tags, codes, n_reads, threads, n_dev, expect_extracted
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def other_configs(ctx, threads, quick=False):
+    """BASELINE.json configs 3, 4, 5 and one paired-end file run on this GPU (the headline line stays cfg2): kernel-only
+    reads/s and GCUPS with CUDA events, the live-op roofline fraction of the dominant kernel, and a parity count of a read
+    sample against the UNMODIFIED reference's run_pHMM (oracle/_ref, the checker -- nothing timed here runs on it)."""
+    import torch
+    from tagdust_b200 import stream
+    from tagdust_b200.api import MODE_GET_LABEL, compile_architecture, live_ops
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refharness
+    R = refharness.RefHarness() if refharness.have_ref() else None
+    tags_all = synth.load_tags(TAGS)
+    pk, _ = peaks()
+    fp32_peak = 148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6
+    WAVE = 148 * 512
+    kw = dict(threshold=THRESHOLD, minlen=16, dust=100)
+    out = {}
+
+    def label_config(name, what, segs, codes, lens, waves):
+        n = WAVE * waves
+        desc = compile_architecture(segs, background(), float(READ_LEN), READ_LEN)
+        model = ctx.model(desc, READ_LEN)
+        b = ctx.batch(n, READ_LEN)
+        b.append(codes[:n], lens[:n])
+        ctx.upload(b)
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            ctx.decode_resident(model, b, MODE_GET_LABEL, stream=st, **kw)
+        torch.cuda.synchronize()
+        ctx.profile_enable(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        ev0.record()
+        for _ in range(reps):
+            ctx.decode_resident(model, b, MODE_GET_LABEL, stream=st, **kw)
+        ev1.record()
+        torch.cuda.synchronize()
+        dt = ev0.elapsed_time(ev1) / 1000.0 / reps
+        prof = ctx.profile_read(0)
+        ctx.profile_enable(False)
+        res = ctx.download(b)
+        lo = live_ops(desc)
+        live = {"k_backward": 9 * lo["ls_bwd"] + lo["add_bwd"], "k_forward": 9 * lo["ls_fwd"] + lo["add_fwd"], "k_label": 0.0}
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        dom_s = prof[dom]["ms"] / 1000.0 / reps
+        cells = 2 * READ_LEN * desc.total_columns
+        rec = {"what": what, "hmms": desc.total_hmms, "columns": desc.total_columns, "reads": n, "value": n / dt, "unit": "reads/s",
+               "gcups": n / dt * cells / 1e9, "cells_per_read": cells,
+               "kernels_ms_per_wave": {k: v["ms"] / v["launches"] for k, v in prof.items()},
+               "roofline": {"kernel": dom, "frac": n * READ_LEN * live[dom] / dom_s / fp32_peak,
+                            "live_logsums_per_hmm_position": (lo["ls_fwd"] if dom == "k_forward" else lo["ls_bwd"]) / desc.total_hmms},
+               "read_type_counts": np.bincount(res["read_type"], minlength=7).tolist()}
+        if R is not None:
+            k = 600 if quick else 1500
+            idx = np.linspace(0, n - 1, k).astype(np.int64)
+            p = R.param_new(segs, threshold=THRESHOLD, minlen=16, dust=100, threads=threads)
+            mb = R.model_new(p, background=background(), average_length=float(READ_LEN), max_seq_len=READ_LEN)
+            want = R.run_phmm(mb, p, 1, codes[idx], lens[idx])
+            R.model_free(mb); R.param_free(p)
+            bad = res["mapq"][idx].view(np.uint32) != want["mapq"].view(np.uint32)
+            for key in ("read_type", "barcode", "fingerprint"):
+                bad |= res[key][idx] != want[key]
+            bad |= (res["labels"][idx][:, :READ_LEN + 1] != want["labels"][:, :READ_LEN + 1]).any(axis=1)
+            rec["parity_vs_reference_run_pHMM"] = {"reads": int(k), "mismatches": int(bad.sum()),
+                                                   "compared": "mapq bits, read_type, barcode, fingerprint, labels"}
+        b.close(); model.close()
+        out[name] = rec
+        log(f"[configs] {name}: {rec['value'] / 1e6:.2f} M reads/s, {rec['gcups']:.0f} GCUPS, parity {rec.get('parity_vs_reference_run_pHMM')}")
+        return desc
+
+    waves = 2 if quick else 4
+    segs3, tags3, codes3, lens3, _ = synth.cfg3_workload(tags_all, WAVE * waves)
+    label_config("cfg3", "read 1 of the paired-end UMI run: -1 F:NNNNNNNN -2 S:<12 nt> -3 B:<95 x 6 nt> -4 R:N, 150 nt", segs3, codes3, lens3, waves)
+    segs4, _, codes4, lens4, _ = synth.cfg4_workload(tags_all, WAVE * waves)
+    label_config("cfg4", "dual index on read 1: -1 B:<24 I7> -2 B:<16 I5> -3 R:N (384 combinations), 150 nt", segs4, codes4, lens4, waves)
+
+    # cfg5: library-prep auto-detection, 64 candidate architectures x 100 000 reads, backward only (MODE_ARCH_COMP)
+    archs = synth.candidate_architectures(tags_all, 16 if quick else 64)
+    descs = [compile_architecture(a, background(), float(READ_LEN), READ_LEN) for a in archs]
+    n5 = 20_000 if quick else 100_000
+    _, tags2 = architecture()
+    codes5, lens5, _ = synth.make_reads_fast(n5, READ_LEN, tags2, error_rate=0.01, random_frac=0.05, seed=5)
+    models = [ctx.model(d, READ_LEN) for d in descs]
+    b = ctx.batch(n5, READ_LEN)
+    b.append(codes5, lens5)
+    ctx.arch_compare(models[:2], b, threads)
+    t0 = time.perf_counter()
+    _, post = ctx.arch_compare(models, b, threads)
+    dt = time.perf_counter() - t0
+    cells5 = float(sum(READ_LEN * d.total_columns for d in descs)) * n5
+    rec = {"what": f"{len(archs)} candidate architectures x {n5} reads, backward() of every read under every architecture, "
+                   f"posteriors summed in {threads} reference thread slices (host arrays in, posteriors out)",
+           "seconds": dt, "value": len(archs) * n5 / dt, "unit": "(architecture, read) pairs/s", "gcups": cells5 / dt / 1e9,
+           "best_architecture": int(np.argmax(post)), "true_architecture": 5}
+    b.close()
+    if R is not None:
+        k = 300 if quick else 1000
+        idx = np.linspace(0, n5 - 1, k).astype(np.int64)
+        bs = ctx.batch(k, READ_LEN)
+        bs.append(codes5[idx], lens5[idx])
+        _, post_s = ctx.arch_compare(models, bs, threads)
+        bs.close()
+        p = R.param_new(archs[0], threads=threads)
+        mbs = []
+        for a in archs:
+            pa = R.param_new(a, threads=threads)
+            mbs.append((R.model_new(pa, background=background(), average_length=float(READ_LEN), max_seq_len=READ_LEN), pa))
+        want = R.run_arch_comp([m for m, _ in mbs], p, codes5[idx], lens5[idx])
+        for m, pa in mbs:
+            R.model_free(m); R.param_free(pa)
+        R.param_free(p)
+        rec["parity_vs_reference_run_pHMM"] = {"reads": int(k), "architectures": len(archs),
+                                               "posterior_bit_mismatches": int((post_s.view(np.uint32) != want.view(np.uint32)).sum()),
+                                               "same_best": bool(int(np.argmax(post_s)) == int(np.argmax(want)))}
+    for m in models:
+        m.close()
+    out["cfg5"] = rec
+    log(f"[configs] cfg5: {rec['seconds']:.2f} s, {rec['gcups']:.0f} GCUPS, {rec.get('parity_vs_reference_run_pHMM')}")
+
+    # paired-end through the streaming demultiplexer: read 1 = cfg3 architecture, read 2 = R:N (run_rna_dust path, host)
+    import shutil
+    import tempfile
+    npair = (300_000 if quick else 2_000_000)
+    tmp = tempfile.mkdtemp(prefix="tdg_bench_pe_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        blk = min(npair, codes3.shape[0])
+        reps = max(1, npair // blk)
+        write_fastq_fixed(os.path.join(tmp, "r1.fq"), codes3[:blk], READ_LEN, reps)
+        rng = np.random.default_rng(9)
+        r2 = rng.integers(0, 4, size=(blk, READ_LEN + 1), dtype=np.uint8)
+        write_fastq_fixed(os.path.join(tmp, "r2.fq"), r2, READ_LEN, reps)
+        desc3 = compile_architecture(segs3, background(), float(READ_LEN), READ_LEN)
+        model3 = ctx.model(desc3, READ_LEN)
+        t0 = time.perf_counter()
+        st = stream.demux_run(ctx, [dict(path=os.path.join(tmp, "r1.fq"), model=model3, num_read_segments=1, threshold=THRESHOLD, max_seq_len=READ_LEN),
+                                    dict(path=os.path.join(tmp, "r2.fq"), model=None, num_read_segments=1, threshold=0.0, max_seq_len=READ_LEN)],
+                              os.path.join(tmp, "out"), barcode_input=0, barcode_names=list(tags3), minlen=16, dust=100, threads=threads)
+        dt = time.perf_counter() - t0
+        model3.close()
+        out["paired_end_files"] = {"what": "2 x 150 nt FASTQ files in /dev/shm -> 2 x 96 demultiplexed files through tdg_demux_run; read 1 carries "
+                                           "UMI + linker + 95 barcodes (cfg3), read 2 is R:N",
+                                   "pairs": int(blk * reps), "seconds": dt, "value": blk * reps / dt, "unit": "read pairs/s",
+                                   "extracted": st["num_EXTRACT_SUCCESS"], "total_read": st["total_read"],
+                                   "stage_busy_s": {k: st[k] for k in ("seconds_split", "seconds_parse", "seconds_gpu_wait", "seconds_write")}}
+        log(f"[configs] paired-end files: {blk * reps / dt / 1e6:.2f} M pairs/s")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def one_context_e2e(ctxN, modelN, codes, lens, kw, steps, n_dev):
     """The C-ABI call with host arrays (pack -> H2D -> kernels -> D2H, double buffered) on ONE context that shards every
     batch over all devices (tdg_plan_shards), driven by one host thread: the library's own multi-device path."""
@@ -480,6 +629,12 @@ def run_gpu_arm(args):
                 modelN.close(); ctxN.close()
         except Exception as exc:  # the streaming layer is an extra line, never a reason to lose the bench
             line["e2e_files"] = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_configs:
+        try:
+            line["configs"] = other_configs(ctx, host_threads(), quick=args.quick_configs)
+        except Exception as exc:
+            import traceback
+            line["configs"] = {"error": repr(exc), "trace": traceback.format_exc()[-600:]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         n_cpu = max(threads * 2500, 20000)   # ~10 s of host work
@@ -520,6 +675,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=32 * 148 * 512, help="reads per step per GPU (default 32 waves)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3/4/5 + paired-end block")
+    ap.add_argument("--quick-configs", action="store_true", help="smaller read sets for the configs block")
     ap.add_argument("--no-files", action="store_true", help="skip the FASTQ-file -> demultiplexed-files measurement")
     ap.add_argument("--files-reads", type=int, default=16_000_000, help="reads of the file-to-files job (strong scaling)")
     args = ap.parse_args()

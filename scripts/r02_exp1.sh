@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
 one() {  # one <tag> <lib suffix or ""> [env...]
 	local tag=$1 suf=$2; shift 2
-	env "$@" TDG_LIB=$PWD/tagdust_b200/libtagdust_b200${suf:+_$suf}.so timeout 600 python bench.py --steps 3 --warmup 3 --reads $((75776*8)) --no-cpu-baseline --no-files 2>gpurun_out/r02_exp1_$tag.err | tee gpurun_out/r02_exp1_$tag.json | python -c "
+	env "$@" TDG_LIB=$PWD/tagdust_b200/libtagdust_b200${suf:+_$suf}.so timeout 600 python bench.py --steps 3 --warmup 3 --reads $((75776*8)) --no-cpu-baseline --no-files --no-configs 2>gpurun_out/r02_exp1_$tag.err | tee gpurun_out/r02_exp1_$tag.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print('$tag', 'value %.3f M/s' % (d['value']/1e6), 'e2e %.3f' % (d['e2e']['value']/1e6), {k:round(v['ms']/v['launches'],3) for k,v in d['kernels_ms'].items()}, 'frac', round(d['roofline']['frac'],3), d['clocks']['sm_mhz'], d['check']['read_type_counts'][:2])"

@@ -7,7 +7,7 @@ for n in $N 1; do
 	if [ $n -gt 1 ]; then
 		TDG_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --steps 5 --warmup 3 --files-reads $FR > gpurun_out/${TAG}_n$n.json 2> gpurun_out/${TAG}_n$n.err
 	else
-		TDG_TRACE=1 timeout 900 python bench.py --gpus 1 --steps 5 --warmup 3 --files-reads $FR --no-cpu-baseline > gpurun_out/${TAG}_n$n.json 2> gpurun_out/${TAG}_n$n.err
+		TDG_TRACE=1 timeout 900 python bench.py --gpus 1 --steps 5 --warmup 3 --files-reads $FR --no-cpu-baseline --no-configs > gpurun_out/${TAG}_n$n.json 2> gpurun_out/${TAG}_n$n.err
 	fi
 	echo "rc=$?"; grep -v trace gpurun_out/${TAG}_n$n.err | grep -v convert_chunk | tail -4
 	python - <<PY

@@ -19,6 +19,7 @@ constexpr int kColRec = 12;    // floats per column record (3 x float4)
 constexpr int kEmitRec = 10;   // eM[5], eI[5]
 constexpr int kMaxSources = 4; // label-DP predecessor sources per HMM (structured form)
 constexpr int kMaxStdCols = 16; // STDU segments with up to this many columns run fully unrolled kernels
+constexpr int kMaxSegCols = 256; // longest segment (columns = nucleotides + 1): the column-loop paths keep 2 floats per column per thread
 
 // Column record layout (floats), see barcode_hmm.h:87-96 for the transition indices:
 //  0 MM  1 MI  2 MD  3 II | 4 IM  5 DD  6 DM  7 MSKIP | 8 ISKIP  9 sM  10 sI  11 live-mask (int bits)
@@ -67,7 +68,8 @@ struct KArgs {
 	int32_t S, H, C;
 	SegInfo seg[kMaxSegments];
 	const float* model_blob;   // device: [colrec C*12][emit C*10]
-	int32_t model_floats;      // floats to stage into shared memory after the logsum table
+	int32_t model_floats;      // floats of the model blob
+	int32_t model_in_smem;     // 1: the blob is staged into shared memory behind the logsum table; 0: read from global memory
 	int32_t dyn_cols;          // columns of shared-memory profile state reserved for the column-loop paths (0 = none)
 	const float* logsum_tab;   // device: 16000 floats, entries >= 15700 zeroed
 	float r_step;              // log(1 - 1/avg) as float   (barcode_hmm.c:4520)

@@ -284,7 +284,7 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 	for (int s = 0; s < S; s++) {
 		SegInfo& g = hm.seg[s];
 		g.nh = d->seg_num_hmms[s]; g.nc = d->seg_num_cols[s];
-		if (g.nh < 1 || g.nc < 1 || g.nc > 64) { snprintf(buf, sizeof buf, "segment %d: %d HMMs x %d columns unsupported (columns 1..64)", s, g.nh, g.nc); err = buf; return TDG_EINVAL; }
+		if (g.nh < 1 || g.nc < 1 || g.nc > kMaxSegCols) { snprintf(buf, sizeof buf, "segment %d: %d HMMs x %d columns unsupported (columns 1..%d)", s, g.nh, g.nc, kMaxSegCols); err = buf; return TDG_EINVAL; }
 		g.colbase = cb; g.hmmbase = hb; g.skip = d->seg_skip[s]; g.skip_live = !is_ninf(g.skip); g.kind = 0;
 		cb += g.nh * g.nc; hb += g.nh;
 	}
@@ -471,6 +471,7 @@ struct tdg_model {
 	std::vector<ModelDev> dev;
 	size_t slot_bytes_full = 0, slot_bytes_bwd = 0;
 	int dyn_cols = 0;  // shared-memory profile state for the column-loop paths, when it fits beside the table and the model
+	int model_in_smem = 1;  // 0: the tables do not fit into shared memory beside the logsum table and are read from global memory
 };
 
 extern "C" int tdg_desc_live_ops(const tdg_model_desc* desc, double out[4])
@@ -532,6 +533,7 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 	if (rc != TDG_OK) { delete m; return fail(rc, "%s", err.c_str()); }
 	const HostModel& hm = m->hm;
 	size_t smem = decode_smem_bytes((int)hm.blob.size(), 0);
+	if (getenv("TDG_MODEL_IN_GLOBAL")) m->model_in_smem = 0;  // tests: force the global-memory tables
 	const size_t W = (size_t)max_len + 2;
 	m->slot_bytes_bwd = (size_t)hm.S * W * 4;
 	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
@@ -540,10 +542,11 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
 		DeviceCtx& d = ctx->devs[k];
 		if (smem + 64 > d.smem_optin) {  // + the kernels' few bytes of static shared memory
-			tdg_model_destroy(m);
-			return fail(TDG_EINVAL, "architecture too large for shared memory: needs %zu B, device allows %zu B", smem, d.smem_optin);
+			// too large to stage (more than ~1 880 columns): the kernels read the tables from global memory instead
+			m->model_in_smem = 0;
+			smem = decode_smem_bytes(0, 0);
 		}
-		if (k == 0 && hm.loop_cols > 0 && decode_smem_bytes((int)hm.blob.size(), hm.loop_cols) + 64 <= d.smem_optin && !getenv("TDG_NO_SMEM_STATE"))
+		if (k == 0 && hm.loop_cols > 0 && decode_smem_bytes(m->model_in_smem ? (int)hm.blob.size() : 0, hm.loop_cols) + 64 <= d.smem_optin && !getenv("TDG_NO_SMEM_STATE"))
 			m->dyn_cols = hm.loop_cols;
 		cudaSetDevice(d.dev);
 		if ((int)smem > d.configured_smem) {
@@ -873,6 +876,7 @@ static void fill_model_args(KArgs& a, const tdg_model* m, int devk, const Device
 	for (int s = 0; s < hm.S; s++) a.seg[s] = hm.seg[s];
 	a.model_blob = m->dev[devk].blob;
 	a.model_floats = (int)hm.blob.size();
+	a.model_in_smem = m->model_in_smem;
 	a.dyn_cols = m->dyn_cols;
 	a.logsum_tab = d.d_tab;
 	a.r_step = hm.r_step; a.r_end = hm.r_end;

@@ -30,7 +30,7 @@
 namespace tdg {
 
 #define NEG_INF (-CUDART_INF_F)
-constexpr int kDynMaxCols = 64;
+constexpr int kDynMaxCols = tdg::kMaxSegCols;  // column-loop paths: thread-local profile state (local memory) for segments up to this long
 constexpr int TDG_MAX_HMMS_DEV = 255;
 
 // ------------------------------------------------------------------------------------------
@@ -150,11 +150,15 @@ struct Smem {
 	float* dyn;           // [2 * dyn_cols][kBlock] profile state of the column-loop paths (this thread's lane), or unused
 };
 
+// GM = the model tables stay in global memory (architectures too large for shared memory); the usual GM = false
+// instantiation keeps the shared-memory pointers the compiler can address with LDS.
+template <bool GM>
 __device__ __forceinline__ Smem stage_smem(const KArgs& a, float* smem)
 {
 	for (int k = threadIdx.x; k < kLogsumSize; k += blockDim.x) smem[k] = a.logsum_tab[k];
 	float* m = smem + kLogsumSize;
-	for (int k = threadIdx.x; k < a.model_floats; k += blockDim.x) m[k] = a.model_blob[k];
+	const int staged = GM ? 0 : a.model_floats;
+	for (int k = threadIdx.x; k < staged; k += blockDim.x) m[k] = a.model_blob[k];
 	// The pre-offset table base is bounced through shared memory so that it reaches the inner
 	// loops as an opaque register: ptxas otherwise re-splits it into (window base, constant) and
 	// spends a second integer add per logsum on the constant.
@@ -163,9 +167,10 @@ __device__ __forceinline__ Smem stage_smem(const KArgs& a, float* smem)
 	__syncthreads();
 	Smem s;
 	s.tab = s_tab_addr;
-	s.colrec = m;
-	s.emit = m + (size_t)a.C * kColRec;
-	s.dyn = m + a.model_floats + threadIdx.x;
+	const float* tables = GM ? a.model_blob : m;
+	s.colrec = tables;
+	s.emit = tables + (size_t)a.C * kColRec;
+	s.dyn = m + staged + threadIdx.x;
 	return s;
 }
 
@@ -429,11 +434,11 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 	}
 }
 
-template <bool STORE>
+template <bool STORE, bool GM = false>
 __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a)
 {
 	extern __shared__ float smem_f[];
-	const Smem sm = stage_smem(a, smem_f);
+	const Smem sm = stage_smem<GM>(a, smem_f);
 	const int slot = blockIdx.x * kBlock + threadIdx.x;
 	const int read = slot;
 	const bool valid = read < a.n_reads;
@@ -694,10 +699,11 @@ __device__ __forceinline__ float s2p_f(float p)
 	return (float)exp((double)p);
 }
 
+template <bool GM = false>
 __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_forward(const KArgs a)
 {
 	extern __shared__ float smem_f[];
-	const Smem sm = stage_smem(a, smem_f);
+	const Smem sm = stage_smem<GM>(a, smem_f);
 	const int slot = blockIdx.x * kBlock + threadIdx.x;
 	const int read = slot;
 	const bool valid = read < a.n_reads;
@@ -1406,25 +1412,34 @@ static int set_dyn_smem(K kernel, int smem_bytes, int cap)
 int kernels_configure(int smem_bytes)
 {
 	int e;
-	if ((e = set_dyn_smem(k_backward<true>, smem_bytes, 0))) return e;
-	if ((e = set_dyn_smem(k_backward<false>, smem_bytes, 0))) return e;
-	if ((e = set_dyn_smem(k_forward, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_backward<true, false>, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_backward<false, false>, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_backward<true, true>, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_backward<false, true>, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_forward<false>, smem_bytes, 0))) return e;
+	if ((e = set_dyn_smem(k_forward<true>, smem_bytes, 0))) return e;
 	if ((e = set_dyn_smem(k_label, smem_bytes, 110 * 1024))) return e;
 	return 0;
 }
 
 int launch_backward(const KArgs& a, bool store, int ctas, void* stream)
 {
-	const size_t smem = decode_smem_bytes(a.model_floats, a.dyn_cols);
-	if (store) k_backward<true><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
-	else k_backward<false><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	const size_t smem = decode_smem_bytes(a.model_in_smem ? a.model_floats : 0, a.dyn_cols);
+	if (a.model_in_smem) {
+		if (store) k_backward<true, false><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+		else k_backward<false, false><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	} else {
+		if (store) k_backward<true, true><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+		else k_backward<false, true><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	}
 	return (int)cudaGetLastError();
 }
 
 int launch_forward(const KArgs& a, int ctas, void* stream)
 {
-	const size_t smem = decode_smem_bytes(a.model_floats, a.dyn_cols);
-	k_forward<<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	const size_t smem = decode_smem_bytes(a.model_in_smem ? a.model_floats : 0, a.dyn_cols);
+	if (a.model_in_smem) k_forward<false><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
+	else k_forward<true><<<ctas, kBlock, smem, (cudaStream_t)stream>>>(a);
 	return (int)cudaGetLastError();
 }
 

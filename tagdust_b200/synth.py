@@ -93,3 +93,57 @@ def make_reads_fast(n, read_len, barcodes, *, error_rate=0.01, random_frac=0.05,
     truth[:n_model] = k
     lens = np.full(n, read_len, dtype=np.int32)
     return codes, lens, truth
+
+
+# ---- the other BASELINE.json configurations, shared by bench.py and the tests -------------------------
+LINKER12 = "ACGTTGCAGTCA"
+
+
+def cfg3_workload(tags, n, seed=2):
+    """cfg3, read 1: UMI (8 uniform nt) + 12-nt linker + barcode (95 tags: 1 + 2 + 96 + 1 = 100 HMMs, the reference's
+    `float total_prob[100]`, barcode_hmm.c:4186) + 124 random nt; read 2 is a plain 150-nt read (R:N, never reaches the HMM)."""
+    tags = list(tags)[:95]
+    segs = ["F:NNNNNNNN", "S:" + LINKER12, "B:" + ",".join(tags), "R:N"]
+    c, lens, truth = make_reads_fast(n, 150, [LINKER12 + t for t in tags], seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    codes = np.zeros_like(c)
+    codes[:, :8] = rng.integers(0, 4, size=(n, 8))
+    codes[:, 8:150] = c[:, :142]
+    return segs, tags, codes, lens, truth
+
+
+def cfg4_workload(tags, n, seed=4):
+    """cfg4, read 1: I7 (24 tags) + I5 (16 tags) + 138 random nt = 384 combinations, -1 B: -2 B: -3 R:N; read 2 R:N."""
+    i7, i5 = list(tags)[:24], list(tags)[24:40]
+    segs = ["B:" + ",".join(i7), "B:" + ",".join(i5), "R:N"]
+    codes, lens, truth = make_reads_fast(n, 150, [a + b for a in i7 for b in i5], seed=seed)
+    return segs, (i7, i5), codes, lens, truth
+
+
+def candidate_architectures(tags, n_arch):
+    """cfg5: distinct candidate architectures for library-prep detection (test_architectures.c): barcode sets of different
+    sizes, with/without UMI, linker, optional G, partial adapters.  Index 5 is the cfg2 architecture (the true one)."""
+    out = []
+    sizes = [4, 8, 12, 16, 24, 32, 48, 64]
+    k = 0
+    while len(out) < n_arch:
+        nb = sizes[k % len(sizes)]
+        variant = (k // len(sizes)) % 8
+        t = tags[(k * 3) % 16:(k * 3) % 16 + nb]
+        b = "B:" + ",".join(t)
+        segs = {
+            0: [b, "R:N"],
+            1: ["F:NNNN", b, "R:N"],
+            2: [b, "S:GGG", "R:N"],
+            3: ["O:N", b, "R:N"],
+            4: ["F:NNNNNNNN", "S:" + LINKER12, b, "R:N"],
+            5: ["S:" + LINKER12[:6], b, "R:N"],
+            6: [b, "R:N", "S:TTTTTT"],
+            7: ["G:G", b, "S:T", "R:N"],
+        }[variant]
+        out.append(segs)
+        k += 1
+    if n_arch > 5:
+        out[5] = ["B:" + ",".join(tags[:48]), "R:N"]
+    assert len({tuple(x) for x in out}) == n_arch
+    return out

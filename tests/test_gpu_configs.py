@@ -85,31 +85,7 @@ def test_cfg4_dual_index(gpu_ctx, oracle):
 
 
 def candidate_architectures(n_arch):
-    """Distinct candidate architectures for library-prep detection (test_architectures.c): barcode sets of
-    different sizes, with/without UMI, linker, optional G, partial adapters.  Index 5 is the true one."""
-    out = []
-    sizes = [4, 8, 12, 16, 24, 32, 48, 64]
-    k = 0
-    while len(out) < n_arch:
-        nb = sizes[k % len(sizes)]
-        variant = (k // len(sizes)) % 8
-        tags = TAGS6_ED3[(k * 3) % 16:(k * 3) % 16 + nb]
-        b = "B:" + ",".join(tags)
-        segs = {
-            0: [b, "R:N"],
-            1: ["F:NNNN", b, "R:N"],
-            2: [b, "S:GGG", "R:N"],
-            3: ["O:N", b, "R:N"],
-            4: ["F:NNNNNNNN", "S:" + LINKER, b, "R:N"],
-            5: ["S:" + LINKER[:6], b, "R:N"],
-            6: [b, "R:N", "S:TTTTTT"],
-            7: ["G:G", b, "S:T", "R:N"],
-        }[variant]
-        out.append(segs)
-        k += 1
-    out[5] = ["B:" + ",".join(TAGS6_ED3[:48]), "R:N"]
-    assert len({tuple(s) for s in out}) == n_arch
-    return out
+    return synth.candidate_architectures(TAGS6_ED3, n_arch)
 
 
 def test_cfg5_architecture_detection(gpu_ctx, oracle):
