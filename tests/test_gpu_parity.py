@@ -337,3 +337,61 @@ def test_spans_with_window(gpu_ctx, ref):
     want = spans_from_labels(out["labels"], lens, desc, out["extracted"], out["spans"].shape[1])
     assert np.array_equal(out["spans"], want)
     ref.model_free(mb); ref.param_free(p)
+
+
+def _rand_tags(rng, n, L):
+    seen, out = set(), []
+    while len(out) < n:
+        t = "".join(rng.choice(list("ACGT"), size=L))
+        if t not in seen:
+            seen.add(t); out.append(t)
+    return out
+
+
+def test_long_linker_segment_90_columns(gpu_ctx, oracle):
+    """A 90-nt S: linker (90-column HMMs): beyond the unrolled and the shared-memory-state paths, the column loop keeps
+    its profile state in thread-local memory (the reference allocates any length, barcode_hmm.c:4591-4674)."""
+    from refharness import background_logp
+    from tagdust_b200 import synth
+    from tagdust_b200.api import compile_architecture
+    rng = np.random.default_rng(77)
+    linker = "".join(rng.choice(list("ACGT"), size=90))
+    tags = ["ACGTAC", "TTGACC", "GGCATT", "CATGCA", "TACGGA", "AGTCTG"]
+    segs = ["S:" + linker, "B:" + ",".join(tags), "R:N"]
+    desc = compile_architecture(segs, background_logp((2501.0, 2480.0, 2510.0, 2492.0, 21.0)), 150.0, 160)
+    assert max(desc.seg_num_cols) >= 90
+    codes, lens, _ = synth.make_reads(700, 150, [linker + t for t in tags], error_rate=0.02, random_frac=0.1, seed=5, len_jitter=4, n_frac=0.005)
+    ora = oracle.run(desc, MODE_GET_LABEL, codes, lens, threshold=1.0, minlen=16, dust=100, threads=8)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.0, minlen=16, dust=100)
+    rep = compare(gpu, ora, lens, MODE_GET_LABEL, "s90")
+    assert all(v == 0 for v in rep.values()), rep
+    assert (gpu["read_type"] == 0).mean() > 0.7
+
+
+@pytest.mark.parametrize("forced", [False, True])
+def test_model_larger_than_shared_memory(gpu_ctx, oracle, monkeypatch, forced):
+    """130 sixteen-nt barcodes: 131 x 16 + 1 = 2 097 columns, more than fit beside the logsum table in shared memory
+    (~1 880): the kernels read the tables from global memory.  H = 132 is beyond the reference's `total_prob[100]`, so the
+    check is against the port.  forced=True sends a small model down the same kernels (TDG_MODEL_IN_GLOBAL)."""
+    from refharness import background_logp
+    from tagdust_b200 import synth
+    from tagdust_b200.api import compile_architecture
+    rng = np.random.default_rng(78)
+    if forced:
+        monkeypatch.setenv("TDG_MODEL_IN_GLOBAL", "1")
+        tags = _rand_tags(rng, 6, 8)
+        n, L = 900, 60
+    else:
+        tags = _rand_tags(rng, 130, 16)
+        n, L = 400, 80
+    segs = ["B:" + ",".join(tags), "R:N"]
+    desc = compile_architecture(segs, background_logp((2501.0, 2480.0, 2510.0, 2492.0, 21.0)), float(L), L + 8)
+    if not forced:
+        assert desc.total_columns > 2000 and desc.total_hmms == 132
+    codes, lens, truth = synth.make_reads(n, L, tags, error_rate=0.02, random_frac=0.1, seed=6, len_jitter=3)
+    ora = oracle.run(desc, MODE_GET_LABEL, codes, lens, threshold=1.0, minlen=16, dust=100, threads=8)
+    gpu = run_gpu(gpu_ctx, desc, codes, lens, MODE_GET_LABEL, threshold=1.0, minlen=16, dust=100)
+    rep = compare(gpu, ora, lens, MODE_GET_LABEL, "bigmodel")
+    assert all(v == 0 for v in rep.values()), rep
+    sel = (gpu["read_type"] == 0) & (truth >= 0)
+    assert sel.sum() > 0.6 * (truth >= 0).sum() and ((gpu["barcode"][sel] & 0xFFFF) == truth[sel]).mean() > 0.98

@@ -354,3 +354,37 @@ def test_demux_tiny_chunks_and_pipes(tmp_path, gz):
     assert st["total_read"] == 4321
     for name in ("out.fq", "out_un.fq"):
         assert filecmp.cmp(os.path.join(cpu, name), os.path.join(mine, name), shallow=False), name
+
+
+def test_dropin_binary_host_only_run_with_interposed_reader(tmp_path):
+    """The drop-in binary (reference CLI + integration/*.c) on an architecture that never reaches the HMM (-1 R:N on two
+    paired files, fixed -Q): no GPU is needed, so this runs here.  It exercises the interposed io_handler /
+    read_fasta_fastq (integration/reader_fast.c: the read-name order check of the controller reads its 1000 entries
+    through tdg_fastq_next), the fast get_sequence_stats and the host-only path of tdg_demux_run, byte for byte against
+    the reference CLI."""
+    gpu_bin = os.path.join(ROOT, "integration", "_build", "tagdust_gpu_rtest")
+    if not have_ref() or not os.path.exists(gpu_bin):
+        pytest.skip("oracle/_ref or integration/_build not built")
+    rng = np.random.default_rng(21)
+    recs1 = random_records(rng, 3300, lo=30, hi=90)
+    recs2 = [(n.replace(" 1:N", " 2:N"), s, q) for n, s, q in random_records(rng, 3300, lo=30, hi=90)]
+    recs2 = [(a[0], b[1], b[2]) for a, b in zip(recs1, recs2)]            # same names (paired files)
+    write_fastq(tmp_path / "r1.fq", recs1)
+    write_fastq(tmp_path / "r2.fq", recs2)
+    outs = {}
+    for tag, binary in (("cpu", f"{REFDIR}/tagdust_rtest"), ("gpu", gpu_bin)):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run(f"{binary} -seed 42 -t 3 -Q 10 -1 R:N r1.fq r2.fq -o {d}/out", cwd=tmp_path, shell=True, capture_output=True, text=True)
+        assert r.returncode == 0, f"{tag}: {r.stderr}"
+        outs[tag] = sorted(glob.glob(str(d / "out*.fq")))
+    assert [os.path.basename(x) for x in outs["cpu"]] == [os.path.basename(x) for x in outs["gpu"]] and len(outs["cpu"]) == 4
+    for a, b in zip(outs["cpu"], outs["gpu"]):
+        assert filecmp.cmp(a, b, shallow=False), os.path.basename(a)
+    # files in different order are refused by both (compare_read_names on the interposed reader's entries)
+    write_fastq(tmp_path / "r3.fq", [(f"other{k}", s, q) for k, (n, s, q) in enumerate(recs2)])
+    codes = []
+    for binary in (f"{REFDIR}/tagdust_rtest", gpu_bin):
+        r = subprocess.run(f"{binary} -seed 42 -t 3 -Q 10 -1 R:N r1.fq r3.fq -o {tmp_path}/bad", cwd=tmp_path, shell=True, capture_output=True, text=True)
+        codes.append(r.returncode != 0)
+    assert codes[0] == codes[1]
