@@ -39,6 +39,20 @@
 
 typedef int (*controller_fn)(struct parameters*);
 
+#include <time.h>
+/* TDG_VERBOSE: wall-clock marks of the controller's phases on stderr */
+static double phase_t0 = 0;
+static void phase(const char* what)
+{
+	struct timespec ts;
+	double t;
+	if (!getenv("TDG_VERBOSE")) return;
+	clock_gettime(CLOCK_REALTIME, &ts);
+	t = ts.tv_sec + 1e-9 * ts.tv_nsec;
+	if (phase_t0 == 0) phase_t0 = t;
+	fprintf(stderr, "tagdust_b200: [%8.3f s, epoch %.3f] %s\n", t - phase_t0, t, what);
+}
+
 static void say(struct parameters* param, const char* fmt, ...)
 {
 	va_list ap;
@@ -83,6 +97,7 @@ int hmm_controller_multiple(struct parameters* param)
 		return ref(param);
 	}
 
+	phase("controller start");
 	tdg_shim_warmup();
 	struct sequence_stats_info** ssi = calloc(nf, sizeof *ssi);
 	struct model_bag** bags = calloc(nf, sizeof *bags);
@@ -132,6 +147,7 @@ int hmm_controller_multiple(struct parameters* param)
 	param->num_query = 1000001;
 #endif
 
+	phase("architectures chosen");
 	/* ---- sequence statistics, thresholds, models: the reference's own functions (:180-207) */
 	{
 		struct read_info** ri = NULL;
@@ -143,6 +159,7 @@ int hmm_controller_multiple(struct parameters* param)
 		}
 		free_read_info(ri, param->num_query);
 	}
+	phase("sequence statistics done");
 	if (!param->confidence_threshold) {
 		for (i = 0; i < nf; i++) {
 			say(param, "Determining threshold for read%d.\n", i);
@@ -160,6 +177,7 @@ int hmm_controller_multiple(struct parameters* param)
 		bags[i] = init_model_bag(param, ssi[i]);
 	}
 
+	phase("thresholds and models done");
 	/* ---- read-name order check of the first chunk (:271-287) on the first 1000 entries of every file */
 	if (nf > 1) {
 		struct read_info*** head = calloc(nf, sizeof *head);
@@ -266,7 +284,9 @@ int hmm_controller_multiple(struct parameters* param)
 			const char* e = getenv("TDG_CHUNK_READS");
 			if (e && atoi(e) > 0) job.chunk_reads = atoi(e);
 		}
+		phase("streaming job starts");
 		rc = tdg_demux_run(ctx, &job, &st);
+		phase("streaming job done");
 		free(in);
 		if (rc != TDG_OK) {
 			say(param, "%s\n", tdg_last_error());
@@ -301,6 +321,7 @@ int hmm_controller_multiple(struct parameters* param)
 	}
 
 DONE:
+	phase("controller returns");
 	tdg_shim_warmup_join();
 	for (i = 0; i < nf; i++) {
 		if (bags[i]) free_model_bag(bags[i]);

@@ -750,7 +750,19 @@ static inline void pack_read(tdg_batch* b, int r, const uint8_t* codes, int len)
 	int pos = 0;
 	for (int w = 0; w < b->words; w++) {
 		uint32_t v = 0;
-		for (int k = 0; k < 8 && pos < total; k++, pos++) v |= (uint32_t)(codes[pos] & 0xF) << (4 * k);
+		if (pos + 8 <= total) {
+			// eight codes at once: keep the low nibble of every byte and fold the bytes together pairwise
+			uint64_t x;
+			memcpy(&x, codes + pos, 8);
+			x &= 0x0F0F0F0F0F0F0F0FULL;
+			x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;
+			x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+			x = (x | (x >> 16)) & 0x00000000FFFFFFFFULL;
+			v = (uint32_t)x;
+			pos += 8;
+		} else {
+			for (int k = 0; k < 8 && pos < total; k++, pos++) v |= (uint32_t)(codes[pos] & 0xF) << (4 * k);
+		}
 		base[(size_t)w * 32] = v;
 	}
 	b->h_len[r] = len;

@@ -97,6 +97,25 @@ struct NucTable {
 };
 const NucTable kNuc;
 
+// Length of the prefix of s[0..n) without a control character (iscntrl() in the C locale: < 32 or 127), eight bytes at
+// a time: the reference stops names, sequences and qualities at the first one (io.c:1716-1790).
+inline uint32_t ctl_span(const uint8_t* s, uint32_t n)
+{
+	uint32_t i = 0;
+	const uint64_t k7f = 0x7F7F7F7F7F7F7F7FULL, k80 = 0x8080808080808080ULL, k01 = 0x0101010101010101ULL;
+	while (i + 8 <= n) {
+		uint64_t x;
+		memcpy(&x, s + i, 8);
+		const uint64_t ge20 = ((x & k7f) + 0x6060606060606060ULL) | x;   // high bit per byte: low 7 bits >= 0x20, or byte >= 0x80
+		const uint64_t z = x ^ k7f;
+		const uint64_t m = (~ge20 & k80) | ((z - k01) & ~z & k80);         // bytes < 0x20, bytes == 0x7F
+		if (m) return i + (uint32_t)(__builtin_ctzll(m) >> 3);
+		i += 8;
+	}
+	while (i < n && !kNuc.ctl[s[i]]) i++;
+	return i;
+}
+
 bool has_suffix(const std::string& s, const char* suf)
 {
 	const size_t n = strlen(suf);
@@ -522,6 +541,7 @@ static int convert_chunk(ParsedChunk& pc, int threads)
 		pc.name_off[r] = no; no += (uint64_t)R.name_n;  // '@' dropped, NUL added
 	}
 	pc.name_off[n] = no;
+	pc.codes.reserve(so + 8);   // slack: the packer reads whole 8-byte words
 	pc.codes.resize(so);
 	if (!f->fasta) pc.qual.resize(so); else pc.qual.clear();
 	pc.names.resize(no);
@@ -537,24 +557,23 @@ static int convert_chunk(ParsedChunk& pc, int threads)
 			{
 				const uint8_t* s = (const uint8_t*)base + R.name + 1;
 				char* d = pc.names.data() + pc.name_off[r];
-				uint32_t i = 0;
-				const uint32_t lim = R.name_n ? R.name_n - 1 : 0;
-				while (i < lim && !kNuc.ctl[s[i]]) { d[i] = (char)s[i]; i++; }
+				const uint32_t i = ctl_span(s, R.name_n ? R.name_n - 1 : 0);
+				memcpy(d, s, i);
 				d[i] = 0;
 			}
 			uint8_t* c = pc.codes.data() + pc.seq_off[r];
 			const uint8_t* s = (const uint8_t*)base + R.seq;
-			uint32_t i = 0;
-			while (i < R.seq_n && !kNuc.ctl[s[i]]) { c[i] = kNuc.code[s[i]]; i++; }
+			const uint32_t i = ctl_span(s, R.seq_n);
+			for (uint32_t k = 0; k < i; k++) c[k] = kNuc.code[s[k]];
 			c[i] = 0;
 			pc.len[r] = (int32_t)i;
 			if ((int)i > mx) mx = (int)i;
 			if (!fasta) {
 				uint8_t* q = pc.qual.data() + pc.seq_off[r];
 				const uint8_t* s2 = (const uint8_t*)base + R.qual;
-				uint32_t k = 0;
-				while (k < R.qual_n && !kNuc.ctl[s2[k]]) { if (k <= i) q[k] = s2[k]; k++; }
+				const uint32_t k = ctl_span(s2, R.qual_n);
 				if (k != i) { int exp = -1; bad.compare_exchange_strong(exp, (int)r); }
+				else memcpy(q, s2, i);
 				q[i] = 0;
 			}
 		}
@@ -838,8 +857,10 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			tdg_model_read_hmms(job->inputs[i].model, is_read[i].data());
 		}
 
-	constexpr int NSLOT = 3;
-	std::vector<Slot> slots(NSLOT);
+	// chunks in flight: one per stage (split, convert+pack, two on the GPU, write) so that no stage waits for a free slot
+	// when the stages take about the same time (several devices); with one device the GPU stage dominates and 4 are enough
+	const int NSLOT = ndev >= 4 ? 6 : 4;
+	std::vector<Slot> slots((size_t)NSLOT);
 	for (auto& s : slots) { s.pc.resize(NI); s.batch.assign(NI, nullptr); s.batch_reads.assign(NI, 0); s.batch_len.assign(NI, 0); s.res.resize(NI); }
 	Queue<int> q_free, q_conv, q_gpu, q_write;
 	for (int k = 0; k < NSLOT; k++) q_free.push(k);
@@ -1131,7 +1152,9 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			// different files go out in parallel: the copies into the page cache are the cost of this stage
 			{
 				std::atomic<int> next{0};
-				parallel_for(std::min(threads, 8), (size_t)std::min(threads, 8), 0, [&](size_t, size_t, int) {
+				// (copies into the page cache: one thread per file, as many files at once as there are threads)
+				const int wt = std::max(1, std::min(std::min(threads, num_outfiles), 64));
+				parallel_for(wt, (size_t)wt, 0, [&](size_t, size_t, int) {
 					for (;;) {
 						const int f = next.fetch_add(1);
 						if (f >= num_outfiles) break;
