@@ -34,11 +34,21 @@ void orc_logsum_table(float* out)
 	memcpy(out, orc_table, sizeof(orc_table));
 }
 
+#ifdef ORC_LS_TRACE
+/* scripts/ls_index_hist.py: the table index of every logsum call, in call order (0xFFFF: an operand was -inf,
+ * 0xFFFE: difference >= 15.7 -- the two cases in which the reference does not touch the table) */
+unsigned short* orc_ls_trace = 0; long orc_ls_trace_n = 0, orc_ls_trace_cap = 0;
+static void ls_trace(unsigned short v) { if (orc_ls_trace && orc_ls_trace_n < orc_ls_trace_cap) orc_ls_trace[orc_ls_trace_n++] = v; }
+#endif
+
 /* misc.c:72-78 logsum; HMMER3_MAX/MIN are ?: macros (misc.h:60,66) */
 float orc_logsum(float a, float b)
 {
 	const float max = (a > b) ? a : b;
 	const float min = (a < b) ? a : b;
+#ifdef ORC_LS_TRACE
+	ls_trace(min == -HUGE_VAL ? 0xFFFF : ((max - min) >= 15.7f ? 0xFFFE : (unsigned short)(int)((max - min) * 1000.0f)));
+#endif
 	return (min == -HUGE_VAL || (max - min) >= 15.7f) ? max : max + orc_table[(int)((max - min) * 1000.0f)];
 }
 #define LS orc_logsum

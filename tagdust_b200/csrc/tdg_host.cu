@@ -907,6 +907,15 @@ static void fill_model_args(KArgs& a, const tdg_model* m, int devk, const Device
 // (threshold calibration emits reads several times the average length) would not fit in HBM.
 static int plan_wave_ctas(const tdg_model* m, const DeviceCtx& d, bool full, int n_reads)
 {
+	// the arena already holds what a full wave (or this whole shard) needs: no cudaMemGetInfo (it takes milliseconds per
+	// device and waits behind concurrent allocations) on the per-chunk path
+	{
+		const long need = std::max(1, (n_reads + kBlock - 1) / kBlock);
+		long want = std::min<long>(d.ctas, need);
+		if (const char* e = getenv("TDG_WAVE_CTAS")) { const long cap = atol(e); if (cap > 0) want = std::min(want, cap); }
+		const size_t bytes = (size_t)num_lanes() * ((size_t)want * kBlock * (full ? m->slot_bytes_full : m->slot_bytes_bwd) + 10 * 256);
+		if (d.scratch && bytes <= d.scratch_bytes) return (int)want;
+	}
 	size_t free_b = 0, total_b = 0;
 	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return d.ctas; }
 	const double budget = 0.90 * (double)(free_b + d.scratch_bytes);

@@ -799,11 +799,13 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	for (int i = 0; i < NI; i++) any_model |= job->inputs[i].model != nullptr;
 	if (any_model && !ctx) return failf(TDG_EINVAL, "tdg_demux_run: a GPU context is required");
 	const int threads = std::max(1, job->threads);
-	// default chunk: two waves per device of the context (a chunk is sharded contiguously over the devices)
+	// default chunk: two waves (one with >= 4 devices) per device of the context; a chunk is sharded contiguously over the devices
 	const int ndev = ctx ? std::max(1, tdg_device_count(ctx)) : 1;
 	// with -ref a chunk is one chunk of the reference's own loop: its thread slices decide how each read is matched
 	const int chunk_reads = job->refset ? (job->ref_chunk_reads > 0 ? job->ref_chunk_reads : 1000001)
-	                                    : (job->chunk_reads > 0 ? job->chunk_reads : 2 * 148 * 512 * ndev);
+	                                    : (job->chunk_reads > 0 ? job->chunk_reads : (ndev >= 4 ? 1 : 2) * 148 * 512 * ndev);
+	// (one wave per device when there are many: the pinned staging of a slot is created at ~1.5 GB/s, and a chunk of
+	//  1.2 M reads per slot would keep the pipeline waiting for its slots for most of a short job)
 	if (job->refset && !ctx) return failf(TDG_EINVAL, "tdg_demux_run: a GPU context is required for the artifact filter");
 	const int nalt = job->num_alternatives;
 	if (nalt < 2) return failf(TDG_EINVAL, "num_alternatives must be >= 2");
@@ -816,8 +818,10 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	const int num_outfiles = nalt * num_out_reads;
 	if (num_outfiles == 0)
 		return failf(TDG_EINVAL, "ERROR: No output files to create. Input sequences may not contain extractable reads or may not match the expected architecture.");
-	std::vector<FILE*> files((size_t)num_outfiles, nullptr);
-	auto close_files = [&] { for (FILE* f : files) if (f) fclose(f); };
+	// plain descriptors + pwrite at offsets kept here: every worker thread writes its own part of every file
+	std::vector<int> files((size_t)num_outfiles, 0);     // 0 = no such file (fd + 1 otherwise)
+	std::vector<int64_t> file_off((size_t)num_outfiles, 0);
+	auto close_files = [&] { for (int f : files) if (f) close(f - 1); };
 	{
 		const bool bc = job->barcode_names != nullptr && job->barcode_input >= 0;
 		char name[4096];
@@ -835,8 +839,9 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					else if (j == 0) { if (num_out_reads > 1) snprintf(name, sizeof name, "%s_READ%d.fq", job->outfile, i + 1); else snprintf(name, sizeof name, "%s.fq", job->outfile); }
 					else { c++; continue; }
 				}
-				files[c] = fopen(name, "w");
-				if (!files[c]) { close_files(); return failf(TDG_EIO, "Failed to open file:%s", name); }
+				const int fd = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+				if (fd < 0) { close_files(); return failf(TDG_EIO, "Failed to open file:%s", name); }
+				files[c] = fd + 1;
 				c++;
 			}
 		}
@@ -1148,20 +1153,46 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					}
 				}
 			});
-			// every file is written by one thread (its per-thread buffers in thread order = input order);
-			// different files go out in parallel: the copies into the page cache are the cost of this stage
+			// Every file keeps input order: the part thread t formatted (reads [b_t, e_t) of the chunk) goes behind the parts
+			// of the threads before it.  The offsets follow from the buffer sizes, so all threads write at once with
+			// pwrite(), each its own (cache-warm) buffers, starting at a different file to stay off each other's inode locks.
 			{
-				std::atomic<int> next{0};
-				// (copies into the page cache: one thread per file, as many files at once as there are threads)
-				const int wt = std::max(1, std::min(std::min(threads, num_outfiles), 64));
-				parallel_for(wt, (size_t)wt, 0, [&](size_t, size_t, int) {
-					for (;;) {
-						const int f = next.fetch_add(1);
-						if (f >= num_outfiles) break;
-						if (!files[f]) continue;
-						for (int t = 0; t < threads; t++) {
-							OutBuf& b = ob[t][f];
-							if (b.n && fwrite(b.d.data(), 1, b.n, files[f]) != b.n) { sh.fail(TDG_EIO, "write error on an output file"); break; }
+				std::vector<int64_t> pos((size_t)threads * num_outfiles);
+				for (int f = 0; f < num_outfiles; f++) {
+					int64_t off = file_off[f];
+					for (int t = 0; t < threads; t++) { pos[(size_t)t * num_outfiles + f] = off; off += (int64_t)ob[t][f].n; }
+					file_off[f] = off;
+				}
+				// one writer per file at a time (the kernel serialises writers of one inode anyway, and a queue of waiters on
+				// its lock is slower than looking for another file): a thread walks its files starting at its own offset and
+				// comes back later to the ones that were busy
+				std::vector<std::atomic<char>> busy((size_t)num_outfiles);
+				for (auto& b : busy) b.store(0);
+				parallel_for(threads, (size_t)threads, 0, [&](size_t tb, size_t te, int) {
+					for (size_t t = tb; t < te; t++) {
+						const int f0 = (int)((t * (size_t)num_outfiles) / (size_t)threads);
+						std::vector<int> todo;
+						for (int q = 0; q < num_outfiles; q++) {
+							const int f = (f0 + q) % num_outfiles;
+							if (files[f] && ob[t][f].n) todo.push_back(f);
+						}
+						while (!todo.empty() && !sh.failed) {
+							size_t kept = 0;
+							for (size_t q = 0; q < todo.size(); q++) {
+								const int f = todo[q];
+								char expect = 0;
+								if (!busy[f].compare_exchange_strong(expect, 1, std::memory_order_acquire)) { todo[kept++] = f; continue; }
+								OutBuf& bf = ob[t][f];
+								size_t done = 0;
+								while (done < bf.n) {
+									const ssize_t w = pwrite(files[f] - 1, bf.d.data() + done, bf.n - done, (off_t)(pos[t * num_outfiles + f] + (int64_t)done));
+									if (w <= 0) { sh.fail(TDG_EIO, "write error on an output file"); break; }
+									done += (size_t)w;
+								}
+								busy[f].store(0, std::memory_order_release);
+							}
+							if (kept == todo.size()) std::this_thread::yield();
+							todo.resize(kept);
 						}
 					}
 				});
