@@ -102,3 +102,23 @@ def test_shard_plan():
             if cnt[k]:
                 assert first[k] == pos and first[k] % 32 == 0
                 pos += cnt[k]
+
+
+def test_live_ops_count_what_the_kernels_execute():
+    """tdg_desc_live_ops (bench.py's roofline numerator): terms whose transition is log(0) are not counted.  cfg2 shape:
+    SURVEY 8d's algorithmic count is 8 + 10 logsums per (column, position) = 108 per 6-column HMM and position; the
+    standard B-segment pattern leaves 47 live."""
+    import bench
+    from tagdust_b200.api import compile_architecture, live_ops
+    segs, _ = bench.architecture()
+    desc = compile_architecture(segs, bench.background(), 150.0, 150)
+    lo = live_ops(desc)
+    H, Cn = desc.total_hmms, desc.total_columns
+    per_hmm = (lo["ls_bwd"] + lo["ls_fwd"]) / H
+    assert 44 < per_hmm < 48, per_hmm
+    assert lo["ls_bwd"] < 8 * Cn and lo["ls_fwd"] < 10 * Cn
+    assert lo["add_bwd"] > 0 and lo["add_fwd"] > 0
+    # a model with a skippable segment and partial adapters has more live terms per column than the standard pattern
+    desc2 = compile_architecture(["P:GGGGGGG", "B:ACGT,TTGA", "O:N", "R:N"], bench.background(), 60.0, 60, five=(7.0, 6.2, 1.1))
+    lo2 = live_ops(desc2)
+    assert lo2["ls_fwd"] / desc2.total_columns > lo["ls_fwd"] / Cn

@@ -27,6 +27,7 @@ WORKER = textwrap.dedent("""
     tall = dist_util.merge_tallies(np.bincount(out["read_type"], minlength=7))
     per_bar = dist_util.merge_tallies(np.bincount((out["barcode"][out["read_type"] == 0] & 0xFFFF), minlength=5))
     dist_util.barrier()
+    dist_util.cpu_barrier()          # the host-side barrier bench.py uses around its rank-0-only strong-scaling leg
     mx = dist_util.max_over_ranks([float(rank + 1), 10.0 - rank])
     if rank == 0:
         full = Oracle().run(desc, MODE_GET_LABEL, codes, lens, threshold=1.5, threads=1)

@@ -165,6 +165,25 @@ def test_architecture_selection_from_arch_file(tmp_path):
     assert "F:NNNN" in log and "Confidence" in log
 
 
+def test_arch_file_with_more_candidates_than_the_model_cache(tmp_path):
+    """30 candidate architectures (the shim's content-keyed model cache holds 24): every model of ab->archs[] must stay
+    alive until tdg_arch_compare returns (the cache used to evict -- and destroy -- models still in use).
+    test_architectures allows up to 99 candidates (MAX_NUM_ARCH 100)."""
+    from cases import TAGS6_ED3
+    from tagdust_b200 import synth
+    tmp = str(tmp_path)
+    make_fastq(os.path.join(tmp, "in.fq"), 2000, [("B", TAGS), ("R", None)], seed=12)
+    archs = synth.candidate_architectures(TAGS6_ED3, 30)
+    archs[7] = [BARC, "R:N"]                      # the true one
+    with open(os.path.join(tmp, "arch.txt"), "w") as fh:
+        for a in archs:
+            fh.write("tagdust " + " ".join(f"-{k + 1} {seg}" for k, seg in enumerate(a)) + "\n")
+    files = run_pair(tmp, "-arch arch.txt in.fq")
+    assert len(files) == len(TAGS) + 1
+    log = open(os.path.join(tmp, "gpu", "out_logfile.txt")).read()
+    assert ",".join(TAGS) in log and "Confidence" in log
+
+
 def write_reference_fasta(path, fq_files, rng, n_from_reads=30):
     """Contaminant sequences: windows of some reads (either strand, some with an edit) plus random ones."""
     comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
