@@ -33,7 +33,8 @@ for kn in dict.fromkeys(n.split("(")[0].split("<")[0].split()[-1] for n in names
     r2 = list(csv.reader(io.StringIO(src)))
     if len(r2) < 3:
         continue
-    h2 = r2[1]; i2 = {h: i for i, h in enumerate(h2)}; d2 = r2[2:]
+    h2 = r2[1]; i2 = {h: i for i, h in enumerate(h2)}
+    d2 = [r for r in r2[2:] if len(r) == len(h2) and r[i2["# Samples"]].strip().isdigit()]
     tot = sum(int(r[i2["# Samples"]]) for r in d2)
     print(f"\n== {kn}: {tot} samples, {len(d2)} SASS instructions; top {topn} by samples")
     for k in sorted(sorted(range(len(d2)), key=lambda k: -int(d2[k][i2["# Samples"]]))[:topn]):
