@@ -682,7 +682,11 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				// k_label loads every posterior (no per-HMM window test), so all of them are stored: a.dp_structured
 				// only keeps the run-time predicate of the earlier window-limited store, which ptxas schedules
 				// measurably better than an unconditional one (k_forward 7.24 vs 7.49 ms per wave on the same day)
+#ifdef TDG_POST_ALWAYS
+				__stcs(pp, P);
+#else
 				if (pfirst != 0xFFFF || a.post_store_all) __stcs(pp, P);
+#endif
 				ps1 = ps0;
 			}
 			csp += kBlock; psp += kBlock; pp += (size_t)a.H * kBlock;

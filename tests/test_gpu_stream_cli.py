@@ -184,6 +184,23 @@ def test_arch_file_with_more_candidates_than_the_model_cache(tmp_path):
     assert ",".join(TAGS) in log and "Confidence" in log
 
 
+def test_reads_shorter_than_the_architecture(tmp_path):
+    """Reads of 2-5 nt under a 6-nt barcode + read architecture: the profile HMMs can
+    delete columns, so the scores stay finite and the reference classifies them (too short / mismatch); the drop-in must
+    write the same files.  (1-nt reads make the CPU reference itself segfault; reads for which b_score is -inf make it
+    index its logsum table with (int)NaN, DESIGN.md section 2: both are outside the contract.)"""
+    tmp = str(tmp_path)
+    rng = np.random.default_rng(13)
+    with open(os.path.join(tmp, "in.fq"), "w") as fh:
+        for r in range(1500):
+            if r % 4 == 0:
+                seq = "".join(rng.choice(list("ACGT"), size=int(rng.integers(2, 6))))
+            else:
+                seq = TAGS[r % len(TAGS)] + "".join(rng.choice(list("ACGT"), size=int(rng.integers(20, 50))))
+            fh.write(f"@s{r}\n{seq}\n+\n{'H' * len(seq)}\n")
+    run_pair(tmp, f"-1 {BARC} -2 R:N in.fq", prefix="short")   # (with F + S + B + R the CPU reference segfaults on these reads)
+
+
 def write_reference_fasta(path, fq_files, rng, n_from_reads=30):
     """Contaminant sequences: windows of some reads (either strand, some with an edit) plus random ones."""
     comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
