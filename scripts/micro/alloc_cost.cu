@@ -1,5 +1,7 @@
 // Allocation costs that decide the start-up of the streaming pipeline: pinned / device allocations of batch size, alone,
 // after a 30 GB scratch arena exists, and from three host threads at once.  nvcc -O2 -o alloc_cost alloc_cost.cu
+#include <sys/mman.h>
+#include <cstring>
 #include <chrono>
 #include <cstdio>
 #include <thread>
@@ -33,6 +35,30 @@ int main()
 		for (int k = 0; k < 3; k++) th.emplace_back([sz] { void* h; cudaHostAlloc(&h, sz, cudaHostAllocPortable); cudaFreeHost(h); });
 		for (auto& t : th) t.join();
 		printf("3 threads x (cudaHostAlloc + cudaFreeHost) %4zu MB: %.4f s total\n", sz >> 20, now() - t0);
+	}
+	// transparent huge pages: anonymous mapping + MADV_HUGEPAGE + first touch, then cudaHostRegister
+	for (size_t sz : sizes) {
+		const size_t al = (sz + (2u << 20) - 1) & ~((size_t)(2u << 20) - 1);
+		double t0 = now();
+		void* p = mmap(nullptr, al, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+		madvise(p, al, MADV_HUGEPAGE);
+		memset(p, 0, al);
+		double t1 = now();
+		cudaError_t e = cudaHostRegister(p, al, cudaHostRegisterPortable);
+		double t2 = now();
+		printf("THP %4zu MB: mmap+madvise+touch %.4f s  cudaHostRegister %.4f s (%s)  total %.2f GB/s\n", sz >> 20, t1 - t0, t2 - t1,
+		       cudaGetErrorString(e), sz / (t2 - t0) / 1e9);
+		cudaHostUnregister(p); munmap(p, al);
+	}
+	for (size_t sz : sizes) {   // the same without the huge-page hint
+		double t0 = now();
+		void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+		memset(p, 0, sz);
+		double t1 = now();
+		cudaHostRegister(p, sz, cudaHostRegisterPortable);
+		double t2 = now();
+		printf("4K  %4zu MB: mmap+touch %.4f s  cudaHostRegister %.4f s  total %.2f GB/s\n", sz >> 20, t1 - t0, t2 - t1, sz / (t2 - t0) / 1e9);
+		cudaHostUnregister(p); munmap(p, sz);
 	}
 	{   // pinned allocation while a 30 GB cudaMalloc runs on another thread
 		cudaFree(big);

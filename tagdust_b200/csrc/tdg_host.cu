@@ -18,6 +18,8 @@
 
 #include <thread>
 
+#include <sys/mman.h>
+
 #include "../../include/tagdust_b200.h"
 #include "../../include/tagdust_b200_stream.h"
 #include "tdg_device.h"
@@ -644,8 +646,58 @@ struct Carver {  // 256-byte aligned offsets into one slab
 	size_t take(size_t bytes) { const size_t o = total; total += (std::max<size_t>(bytes, 1) + 255) / 256 * 256; return o; }
 };
 
+// Pinned host staging.  Large blocks are anonymous mappings with a huge-page hint, touched once and registered with
+// the driver: pinning 2 MB pages runs at ~6 GB/s on this class of host, cudaHostAlloc's 4 KB pages at ~2 GB/s
+// (scripts/micro/alloc_cost.cu, profiles/r02_alloc_cost2.txt) -- the start-up of a multi-GPU streaming job is made of
+// exactly this.  Small blocks, and hosts where the mapping or the registration fails, use cudaHostAlloc.
+struct PinnedBlock { void* p; size_t bytes; bool mapped; };
+static std::mutex g_pin_mu;
+static std::vector<PinnedBlock> g_pinned;   // mapped blocks only: how to release them
+
+static int pinned_bytes(void** out, size_t bytes)
+{
+	bytes = std::max<size_t>(bytes, 1);
+	static const bool no_thp = getenv("TDG_NO_THP") != nullptr;
+	if (bytes >= ((size_t)4 << 20) && !no_thp) {
+		const size_t huge = (size_t)2 << 20;
+		const size_t al = (bytes + huge - 1) / huge * huge;
+		void* q = mmap(nullptr, al, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+		if (q != MAP_FAILED) {
+			madvise(q, al, MADV_HUGEPAGE);
+			madvise(q, al, MADV_DONTFORK);   // the readers popen() zcat / bzcat: DMA-pinned pages stay out of the children
+			memset(q, 0, al);   // first touch: the pages exist before the driver pins them
+			if (cudaHostRegister(q, al, cudaHostRegisterPortable) == cudaSuccess) {
+				std::lock_guard<std::mutex> l(g_pin_mu);
+				g_pinned.push_back({q, al, true});
+				*out = q;
+				return TDG_OK;
+			}
+			cudaGetLastError();
+			munmap(q, al);
+		}
+	}
+	CK(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+	return TDG_OK;
+}
+
+static void pinned_free(void* p)
+{
+	if (!p) return;
+	{
+		std::lock_guard<std::mutex> l(g_pin_mu);
+		for (size_t k = 0; k < g_pinned.size(); k++)
+			if (g_pinned[k].p == p) {
+				cudaHostUnregister(p);
+				munmap(p, g_pinned[k].bytes);
+				g_pinned.erase(g_pinned.begin() + (long)k);
+				return;
+			}
+	}
+	cudaFreeHost(p);
+}
+
 template <class T>
-static int pinned(T** p, size_t n) { CK(cudaHostAlloc((void**)p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocPortable)); return TDG_OK; }
+static int pinned(T** p, size_t n) { return pinned_bytes((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 template <class T>
 static int devalloc(T** p, size_t n) { CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T))); return TDG_OK; }
 
@@ -665,9 +717,9 @@ extern "C" void tdg_batch_destroy(tdg_batch* b)
 		if (s.d2h_done) cudaEventDestroy(s.d2h_done);
 		if (s.copy) cudaStreamDestroy(s.copy);
 	}
-	cudaFreeHost(b->h_slab);
-	cudaFreeHost(b->h_labels);
-	cudaFreeHost(b->h_spans);
+	pinned_free(b->h_slab);
+	pinned_free(b->h_labels);
+	pinned_free(b->h_spans);
 	delete b;
 }
 
@@ -1079,7 +1131,7 @@ static int ensure_span_buffers(tdg_batch* b, int stride)
 		if (b->shard[k].spans) { CK(cudaStreamSynchronize(b->shard[k].copy)); CK(cudaFree(b->shard[k].spans)); b->shard[k].spans = nullptr; }
 		if ((rc = devalloc(&b->shard[k].spans, (size_t)b->shard[k].cap * stride * 2))) return rc;
 	}
-	if (b->h_spans) { CK(cudaFreeHost(b->h_spans)); b->h_spans = nullptr; }
+	if (b->h_spans) { pinned_free(b->h_spans); b->h_spans = nullptr; }
 	if ((rc = pinned(&b->h_spans, (size_t)b->max_reads * stride * 2))) return rc;
 	b->span_cap = stride;
 	return TDG_OK;
@@ -1410,8 +1462,13 @@ void batch_release(tdg_batch* b)
 {
 	if (!b) return;
 	if (b->pending) { tdg_result r; tdg_wait(b, &r); }
-	std::lock_guard<std::mutex> l(b->ctx->pool_mu);
-	b->ctx->pool.push_back(b);
+	tdg_batch* victim = nullptr;
+	{
+		std::lock_guard<std::mutex> l(b->ctx->pool_mu);
+		b->ctx->pool.push_back(b);
+		if (b->ctx->pool.size() > 12) { victim = b->ctx->pool.front(); b->ctx->pool.erase(b->ctx->pool.begin()); }  // oldest goes
+	}
+	if (victim) tdg_batch_destroy(victim);
 }
 
 // Everything the first tdg_submit(MODE_GET_LABEL, want_spans) of `b` under `m` would otherwise allocate on the GPU thread

@@ -679,9 +679,10 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				st_keep(csp, cs, keep);
 				// [pfirst, plast]: the window outside which exp(P) is exactly 0 (k_label skips HMMs without predecessors there)
 				if (!(P < -104.0f)) { plast = i; pfirst = min(pfirst, i); }
-				// k_label loads every posterior (no per-HMM window test), so all of them are stored: a.dp_structured
-				// only keeps the run-time predicate of the earlier window-limited store, which ptxas schedules
-				// measurably better than an unconditional one (k_forward 7.24 vs 7.49 ms per wave on the same day)
+				// k_label loads every posterior (no per-HMM window test), so all of them are stored.  The predicate is always
+				// true (post_store_all = 1) but opaque to the compiler, and ptxas schedules the loop measurably better with
+				// it than with a plain store: k_forward 7.24 vs 7.49 ms per wave in round 1, 7.47 vs 7.68 ms in round 2
+				// (same box, back to back, scripts/gpu_ab.sh postalways; -DTDG_POST_ALWAYS builds the plain store).
 #ifdef TDG_POST_ALWAYS
 				__stcs(pp, P);
 #else
