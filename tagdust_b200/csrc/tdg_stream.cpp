@@ -46,6 +46,7 @@ int batch_acquire(tdg_context* ctx, int max_reads, int max_len, tdg_batch** out)
 void batch_release(tdg_batch* b);
 int batch_prepare(tdg_batch* b, const tdg_model* m, bool host_labels);
 int scratch_prepare(tdg_context* ctx, tdg_model* m);
+int batch_append_text(tdg_batch* b, int n, const char* text, const uint64_t* seq_pos, const int32_t* len, const uint8_t* code_of, int threads);
 }
 
 namespace {
@@ -93,7 +94,9 @@ struct NucTable {
 		code[46] = 5;                                                                             // '.' (nuc_code.c:52)
 		code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['G'] = code['g'] = 2;
 		code['T'] = code['t'] = 3; code['U'] = code['u'] = 3;
+		for (int i = 0; i < 256; i++) out[i] = "ACGTNN"[code[i]];   // print_all's alphabet (io.c:757) of the code of a character
 	}
+	char out[256];
 };
 const NucTable kNuc;
 
@@ -165,6 +168,10 @@ struct ParsedChunk {
 	RawVec<uint64_t> seq_off, name_off;
 	RawVec<uint8_t> codes, qual;
 	RawVec<char> names;
+	// lean form (the demultiplexer): no code / quality / name copies, everything is read from `text` again where it is
+	// needed -- seq_pos / qual_pos / name_pos are text offsets, name_len the name's length up to its first control character
+	RawVec<uint64_t> seq_pos, qual_pos, name_pos;
+	RawVec<uint32_t> name_len;
 	// line table of the sequential pass: offsets into `text`, piece lengths (without the newline)
 	// `next`: text offset right behind the line that completed the entry (the first quality line of a FASTQ entry, the first
 	// sequence line of a FASTA entry) -- where a chunk ends when this is its last entry (io.c:1797-1808)
@@ -585,6 +592,43 @@ static int convert_chunk(ParsedChunk& pc, int threads)
 	return TDG_OK;
 }
 
+// Lean conversion (tdg_demux_run): lengths and validation only.  The 4-bit packing reads the sequence characters from
+// the text (tdg::batch_append_text), the writer formats names / bases / qualities from the text: the intermediate arrays
+// of convert_chunk (about 1.5 x the input in writes, and as much again in reads by the writer) are never made.
+static int lean_chunk(ParsedChunk& pc, int threads)
+{
+	const int n = pc.n;
+	if (n == 0) return TDG_OK;
+	const char* path = pc.path.c_str();
+	pc.len.resize(n); pc.seq_pos.resize(n); pc.qual_pos.resize(n); pc.name_pos.resize(n); pc.name_len.resize(n);
+	const char* base = pc.text;
+	const bool fasta = pc.fasta;
+	std::atomic<int> bad{-1}, noseq{-1}, noqual{-1};
+	std::vector<int> tmax((size_t)std::max(1, threads), 0);
+	parallel_for(threads, (size_t)n, 2048, [&](size_t b, size_t e, int t) {
+		int mx = 0;
+		for (size_t r = b; r < e; r++) {
+			const ParsedChunk::Rec& R = pc.recs[r];
+			if (!R.has_seq) { int exp = -1; noseq.compare_exchange_strong(exp, (int)r); continue; }
+			if (!fasta && !R.has_qual) { int exp = -1; noqual.compare_exchange_strong(exp, (int)r); continue; }
+			pc.name_pos[r] = R.name + 1;
+			pc.name_len[r] = ctl_span((const uint8_t*)base + R.name + 1, R.name_n ? R.name_n - 1 : 0);
+			const uint32_t i = ctl_span((const uint8_t*)base + R.seq, R.seq_n);
+			pc.seq_pos[r] = R.seq;
+			pc.len[r] = (int32_t)i;
+			if ((int)i > mx) mx = (int)i;
+			pc.qual_pos[r] = R.qual;
+			if (!fasta && ctl_span((const uint8_t*)base + R.qual, R.qual_n) != i) { int exp = -1; bad.compare_exchange_strong(exp, (int)r); }
+		}
+		tmax[t] = std::max(tmax[t], mx);
+	});
+	if (noseq.load() >= 0) return failf(TDG_EFORMAT, "%s: entry %d has no sequence line", path, noseq.load());
+	if (noqual.load() >= 0) return failf(TDG_EFORMAT, "%s: entry %d has no quality line", path, noqual.load());
+	if (bad.load() >= 0) return failf(TDG_EFORMAT, "ERROR: Length of sequence and base qualities differ!.");  // io.c:1770
+	for (int v : tmax) pc.max_len = std::max(pc.max_len, v);
+	return TDG_OK;
+}
+
 extern "C" int tdg_fastq_next(tdg_fastq* f, int max_reads, int threads, tdg_fastq_chunk* chunk)
 {
 	if (!f || !chunk) return failf(TDG_EINVAL, "tdg_fastq_next: NULL argument");
@@ -731,6 +775,16 @@ bool dust_low_complexity(const uint8_t* seq, int rlen, int dust_cut)
 	for (int j = 0; j < 64; j++) s += triplet[j] * (triplet[j] - 1.0) / 2.0;
 	s = s / (double)(c - 3) * 10.0;
 	return s > dust_cut;
+}
+
+// the same on the characters of the input text (lean path): residue j is nuc_code[text[j]], 0 behind the read
+bool dust_low_complexity_text(const uint8_t* s, int rlen, int dust_cut)
+{
+	uint8_t seq[72];
+	const int m = rlen < 66 ? rlen : 66;
+	for (int j = 0; j < m; j++) seq[j] = kNuc.code[s[j]];
+	for (int j = m; j < 72; j++) seq[j] = 0;
+	return dust_low_complexity(seq, rlen, dust_cut);
 }
 
 struct OutBuf {
@@ -959,7 +1013,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			bool ok = true;
 			if (!s.last) {
 				for (int i = 0; i < NI && ok; i++)
-					if (convert_chunk(s.pc[i], threads) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
+					if (lean_chunk(s.pc[i], threads) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
 				for (int i = 0; i < NI && ok; i++) {
 					ParsedChunk& pc = s.pc[i];
 					// barcode_hmm.c:293-309: every read at least as long as the running maximum rebuilds the model
@@ -981,7 +1035,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 						if (tdg::batch_acquire(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; break; }
 					}
 					tdg_batch_clear(s.batch[i]);
-					if (tdg_batch_append_ragged(s.batch[i], pc.n, pc.codes.data(), pc.seq_off.data(), pc.len.data(), threads) != TDG_OK) {
+					if (tdg::batch_append_text(s.batch[i], pc.n, pc.text, pc.seq_pos.data(), pc.len.data(), kNuc.code, threads) != TDG_OK) {
 						sh.fail(TDG_EINVAL, tdg_last_error()); ok = false;
 					}
 				}
@@ -1055,7 +1109,6 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			const int n = s.n;
 			for (auto& v : ob) for (auto& b : v) b.n = 0;
 			parallel_for(threads, (size_t)n, 1024, [&](size_t b, size_t e, int t) {
-				static const char alphabet[] = "ACGTNN";
 				std::vector<OutBuf>& out = ob[t];
 				std::vector<int64_t>& tl = tally[t];
 				std::vector<int32_t> rt((size_t)NI), fpv((size_t)NI);
@@ -1078,7 +1131,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 							rt[i] = s.res[i].read_type[r]; fpv[i] = -1; mq[i] = -1.0f;  // run_rna_dust on the device (artifact filter, dust)
 						} else {
 							rt[i] = TDG_EXTRACT_SUCCESS; fpv[i] = -1; mq[i] = -1.0f;  // do_rna_dust + clear_read_info (io.c:2063-2093)
-							if (job->dust && dust_low_complexity(pc.codes.data() + pc.seq_off[r], pc.len[r], job->dust)) rt[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
+							if (job->dust && dust_low_complexity_text((const uint8_t*)pc.text + pc.seq_pos[r], pc.len[r], job->dust)) rt[i] = TDG_EXTRACT_FAIL_LOW_COMPLEXITY;
 						}
 						merged = std::max(merged, rt[i]);
 					}
@@ -1098,11 +1151,11 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					for (int i = 0; i < NI; i++) {
 						if (!job->inputs[i].num_read_segments) continue;
 						const ParsedChunk& pc = s.pc[i];
-						const uint8_t* seq = pc.codes.data() + pc.seq_off[r];
-						const uint8_t* ql = pc.fasta ? nullptr : pc.qual.data() + pc.seq_off[r];
+						const uint8_t* seq = (const uint8_t*)pc.text + pc.seq_pos[r];     // characters; codes through kNuc
+						const uint8_t* ql = pc.fasta ? nullptr : (const uint8_t*)pc.text + pc.qual_pos[r];
 						const int len = pc.len[r];
-						const char* name = pc.names.data() + pc.name_off[r];
-						const size_t name_len = strlen(name);
+						const char* name = pc.text + pc.name_pos[r];
+						const size_t name_len = pc.name_len[r];
 						int f = base_file[i] + sel;
 						// print_all (io.c:923-1001) walks the rewritten read: runs of bases (codes < 5) separated by spacers, one
 						// output record per run, the run behind a spacer goes to the next READ file.  Here the spacers are never
@@ -1115,9 +1168,9 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 							const int s1 = std::min(len, s0 + sl);
 							int g = s0;
 							while (g < s1) {
-								while (g < s1 && seq[g] >= 5) g++;
+								while (g < s1 && kNuc.code[seq[g]] >= 5) g++;
 								int h = g;
-								while (h < s1 && seq[h] < 5) h++;
+								while (h < s1 && kNuc.code[seq[h]] < 5) h++;
 								if (h == g) break;
 								const bool more = h < len;  // something follows the run: the next run goes to the next READ file
 								if (f >= 0 && f < num_outfiles && files[f]) {
@@ -1139,7 +1192,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 									memcpy(p, ";RQ:", 4); p += 4;
 									p += tdg_format_rq(mq[i], p);
 									*p++ = '\n';
-									for (int q = g; q < h; q++) *p++ = alphabet[seq[q]];
+									for (int q = g; q < h; q++) *p++ = kNuc.out[seq[q]];
 									*p++ = '\n'; *p++ = '+'; *p++ = '\n';
 									if (ql) { memcpy(p, ql + g, (size_t)run); p += run; }
 									else { memset(p, '.', (size_t)run); p += run; }
