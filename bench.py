@@ -689,7 +689,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3/4/5 + paired-end block")
     ap.add_argument("--quick-configs", action="store_true", help="smaller read sets for the configs block")
     ap.add_argument("--no-files", action="store_true", help="skip the FASTQ-file -> demultiplexed-files measurement")
-    ap.add_argument("--files-reads", type=int, default=16_000_000, help="reads of the file-to-files job (strong scaling)")
+    ap.add_argument("--files-reads", type=int, default=32_000_000, help="reads of the file-to-files job (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
