@@ -275,7 +275,7 @@ __device__ __forceinline__ float trv(const float* r, const SegInfo& sg, int nc, 
 template <int NC, int KIND, bool STORE, bool SMS = false>
 __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, int x_term, bool last_seg,
-                                            float2* __restrict__ bw, float* __restrict__ sb)
+                                            float2* __restrict__ bw, float* __restrict__ sb, int f_begin = 0)
 {
 	constexpr bool STD = KIND == 1;
 	constexpr int N = Cols<NC, STD>::N;
@@ -291,7 +291,7 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 	const TabAddr tab = sm.tab;
 	const uint64_t keep = make_keep_policy();
 
-	for (int f = 0; f < sg.nh; ++f) {
+	for (int f = f_begin; f < sg.nh; ++f) {
 		const int c0 = sg.colbase + f * nc;
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
 		const float* em = sm.emit + (size_t)c0 * kEmitRec;
@@ -434,6 +434,116 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 	}
 }
 
+// ------------------------------------------------------------------------------------------
+// backward, standard-pattern segment, TWO HMMs per position loop (f, f+1).  Same arithmetic and the same order of the
+// silent-state chain as bwd_segment<NC, 1> run on f and then on f+1 -- cs[i] takes f's term, f's skip term, f+1's term,
+// f+1's skip term -- but cs[i] / ps[i] are loaded and stored once per pair (they are 23 % of k_backward's HBM traffic at
+// cfg2, and k_backward is HBM-bound), the sequence word, the insert emission and the loop bookkeeping are shared, and the
+// two recurrences are independent instruction streams.  An odd last HMM goes through bwd_segment.
+// ------------------------------------------------------------------------------------------
+#ifndef TDG_NO_PAIRS
+template <int NC, bool STORE>
+__device__ __forceinline__ void bwd_pair_std(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
+                                             const SeqReader& rd, int off, int len, int lw, int x_term, bool last_seg,
+                                             float2* __restrict__ bw, float* __restrict__ sb)
+{
+	constexpr int m = NC - 1;
+	constexpr int ncs = NC - 1;
+	const size_t W = (size_t)(a.lmax + 2);
+	float* cs_arr = sb + ((size_t)j * W) * kBlock;
+	const float* ps_arr = sb + ((size_t)(j + 1) * W) * kBlock;
+	const TabAddr tab = sm.tab;
+	const uint64_t keep = make_keep_policy();
+	const float ta = sg.ta, tb = sg.tb, tb2 = sg.tb2, tc = sg.tc, td = sg.td;
+
+	for (int f = 0; f + 1 < sg.nh; f += 2) {
+		const int c0 = sg.colbase + f * NC;
+		const float* emA = sm.emit + (size_t)c0 * kEmitRec;
+		const float* emB = emA + (size_t)NC * kEmitRec;
+		const float sM0A = (sm.colrec + (size_t)c0 * kColRec)[F_SM];
+		const float sM0B = (sm.colrec + (size_t)(c0 + NC) * kColRec)[F_SM];
+		float MA[NC], IA[NC], MB[NC], IB[NC], eMcA[NC], eMcB[NC];
+#pragma unroll
+		for (int g = 0; g < NC; ++g) {
+			MA[g] = NEG_INF; IA[g] = NEG_INF; MB[g] = NEG_INF; IB[g] = NEG_INF;
+			eMcA[g] = emA[g * kEmitRec + x_term]; eMcB[g] = emB[g * kEmitRec + x_term];
+		}
+		float eIc = emA[5 + x_term];   // one insert-emission row for the whole segment (checked by the host)
+		float ps1 = last_seg ? 0.0f : ps_arr[(size_t)(len + 1) * kBlock];
+		SeqDown sd;
+		sd.init(rd, off + lw - 1);
+		float* csp = cs_arr + (size_t)lw * kBlock;
+		const float* psp = ps_arr + (size_t)lw * kBlock;
+		float2* bwpA = bw + ((size_t)c0 * a.lmax + (size_t)(lw - 1) * ncs) * kBlock;
+		float2* bwpB = bwpA + (size_t)NC * a.lmax * kBlock;
+		float cs_n = (lw >= 1) ? ld_keep(csp, keep) : NEG_INF;
+		float ps_n = (!last_seg && lw >= 1) ? ld_keep(psp, keep) : NEG_INF;
+		for (int i = lw; i >= 1; --i) {
+			const int x0 = sd.get();
+			float cs = cs_n;
+			const float ps0 = ps_n;
+			if (i > 1) {
+				cs_n = ld_keep(csp - kBlock, keep);
+				if (!last_seg) ps_n = ld_keep(psp - kBlock, keep);
+			}
+			if (kPrefetchDist > 0 && i > kPrefetchDist) {
+				prefetch_l1(csp - (size_t)kPrefetchDist * kBlock);
+				if (!last_seg) prefetch_l1(psp - (size_t)kPrefetchDist * kBlock);
+			}
+			if (i <= len) {
+				const float eI0 = emA[5 + x0];
+				// one HMM: columns m .. 0 at this position (the same expressions as bwd_segment<NC, 1>)
+				auto hmm = [&](float (&M)[NC], float (&I)[NC], float (&eMc)[NC], const float* em, float sM0, float2* bwp) {
+					float eM0[NC];
+#pragma unroll
+					for (int g = 0; g < NC; ++g) eM0[g] = em[g * kEmitRec + x0];
+					float oldMp = M[m];
+					float newMp = ps1 + 0.0f;   // last column: only MSKIP (= +0) is live
+					float D = NEG_INF;
+					M[m] = newMp; I[m] = NEG_INF;
+#pragma unroll
+					for (int gg = 1; gg < NC; ++gg) {
+						const int g = m - gg, p = g + 1;
+						const float oldMg = M[g];
+						float v = oldMp + eMc[p] + ta;                                             // MM
+						v = LS(v, I[g] + eIc + (g == NC - 2 ? tb2 : tb), tab);                      // MI
+						if (g <= NC - 3) v = LS(v, D + tb, tab);                                    // MD
+						const float nM = v;
+						v = I[g] + tc + eIc;                                                        // II
+						v = LS(v, oldMp + td + eMc[p], tab);                                        // IM
+						const float nI = v;
+						{
+							const bool ldd = (g >= 1 && g <= NC - 3), ldm = (g >= 1);
+							float dv = NEG_INF;
+							if (ldd) dv = D + tc;
+							if (ldm) {
+								const float t = newMp + eM0[p] + (g == NC - 2 ? 0.0f : td);
+								dv = ldd ? LS(dv, t, tab) : t;
+							}
+							D = dv;
+						}
+						if (g == 0) cs = LS(cs, nM + sM0 + eM0[0], tab);                            // SM: column 0 only
+						M[g] = nM; I[g] = nI;
+						oldMp = oldMg; newMp = nM;
+						if (STORE) __stcs(&bwp[(size_t)g * kBlock], make_float2(nM, nI));
+					}
+					if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);
+#pragma unroll
+					for (int g = 0; g < NC; ++g) eMc[g] = eM0[g];
+				};
+				hmm(MA, IA, eMcA, emA, sM0A, bwpA);
+				hmm(MB, IB, eMcB, emB, sM0B, bwpB);
+				st_keep(csp, cs, keep);
+				eIc = eI0;
+				ps1 = ps0;
+			}
+			csp -= kBlock; psp -= kBlock; bwpA -= (size_t)ncs * kBlock; bwpB -= (size_t)ncs * kBlock;
+		}
+	}
+	if (sg.nh & 1) bwd_segment<NC, 1, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last_seg, bw, sb, sg.nh - 1);
+}
+#endif
+
 template <bool STORE, bool GM = false>
 __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a)
 {
@@ -472,6 +582,11 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a
 		const int kind = sg.kind;  // host-selected code path: 0 generic, 1 STD
 		const int nc = sg.nc;
 #define BWD_CASE(NCV, KINDV) bwd_segment<NCV, KINDV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb)
+#ifndef TDG_NO_PAIRS
+#define BWD_PAIR(NCV) do { if (sg.nh >= 2) bwd_pair_std<NCV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb); else BWD_CASE(NCV, 1); } while (0)
+#else
+#define BWD_PAIR(NCV) BWD_CASE(NCV, 1)
+#endif
 // column-loop paths: profile state in shared memory when the host reserved room for this many columns
 #define BWD_LOOP(KINDV)                                                                                          \
 	do {                                                                                                         \
@@ -481,11 +596,11 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a
 		if (kind == 1) {
 			switch (nc) {
 				case 3: BWD_CASE(3, 1); break;
-				case 4: BWD_CASE(4, 1); break;
-				case 5: BWD_CASE(5, 1); break;
-				case 6: BWD_CASE(6, 1); break;
-				case 7: BWD_CASE(7, 1); break;
-				case 8: BWD_CASE(8, 1); break;
+				case 4: BWD_PAIR(4); break;
+				case 5: BWD_PAIR(5); break;
+				case 6: BWD_PAIR(6); break;
+				case 7: BWD_PAIR(7); break;
+				case 8: BWD_PAIR(8); break;
 				case 9: BWD_CASE(9, 1); break;
 				case 10: BWD_CASE(10, 1); break;
 				case 11: BWD_CASE(11, 1); break;
@@ -510,6 +625,7 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a
 			}
 		}
 #undef BWD_CASE
+#undef BWD_PAIR
 #undef BWD_LOOP
 	}
 	if (valid) a.b_score[read] = sb[(size_t)1 * kBlock];  // model[0]->silent_backward[1] (:3610)
@@ -524,7 +640,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
                                             const SeqReader& rd, int off, int len, int lw, float B,
                                             const float2* __restrict__ bw, const float* __restrict__ sbk,
                                             float* __restrict__ sf, float* __restrict__ post, float* __restrict__ tp,
-                                            uint32_t* __restrict__ prange)
+                                            uint32_t* __restrict__ prange, int f_begin = 0)
 {
 	constexpr bool STD = KIND == 1;
 	constexpr int N = Cols<NC, STD>::N;
@@ -542,7 +658,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 	const size_t bstep = (size_t)ncs * kBlock;
 	const uint64_t keep = make_keep_policy();
 
-	for (int f = 0; f < sg.nh; ++f) {
+	for (int f = f_begin; f < sg.nh; ++f) {
 		const int h = sg.hmmbase + f;
 		const int c0 = sg.colbase + f * nc;
 		const float* rec = sm.colrec + (size_t)c0 * kColRec;
@@ -697,6 +813,152 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 	}
 }
 
+// ------------------------------------------------------------------------------------------
+// forward + posterior, standard-pattern segment, TWO HMMs per position loop (see bwd_pair_std): cs[i], ps[i] and the
+// silent_backward value of the next segment are loaded once per pair, the Mb/Ib of HMM f+1 are fetched while HMM f is
+// computed and those of HMM f for the next position while HMM f+1 is computed (one buffer per HMM instead of two).
+// MEASURED AND NOT ADOPTED (round 2, same box back to back): bit-identical, but k_forward 7.65-7.69 ms per wave against
+// 7.39-7.40 ms for the one-HMM loop -- k_forward is bound by issue slots, not by HBM, the shared loads are a small part
+// of its instructions and two HMMs' state plus two Mb/Ib buffers do not fit 128 registers without spills.  Built only with
+// -DTDG_FWD_PAIRS (scripts/build_variant.sh); the backward pass, which IS bound by HBM, uses its pair loop by default.
+// ------------------------------------------------------------------------------------------
+#if defined(TDG_FWD_PAIRS) && !defined(TDG_NO_PAIRS)
+template <int NC>
+__device__ __forceinline__ void fwd_pair_std(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
+                                             const SeqReader& rd, int off, int len, int lw, float B,
+                                             const float2* __restrict__ bw, const float* __restrict__ sbk,
+                                             float* __restrict__ sf, float* __restrict__ post, float* __restrict__ tp,
+                                             uint32_t* __restrict__ prange)
+{
+	constexpr int NB = NC - 1;   // stored columns
+	const bool last_seg = (j == a.S - 1);
+	const bool first_seg = (j == 0);
+	const size_t W = (size_t)(a.lmax + 2);
+	float* cs_arr = sf + ((size_t)j * W) * kBlock;
+	const float* ps_arr = sf + ((size_t)(j - 1) * W) * kBlock;  // only dereferenced when j > 0
+	const TabAddr tab = sm.tab;
+	const int skip_live = sg.skip_live;
+	const size_t bstep = (size_t)NB * kBlock;
+	const uint64_t keep = make_keep_policy();
+	const float ta = sg.ta, tb = sg.tb, tb2 = sg.tb2, tc = sg.tc, td = sg.td;
+
+	for (int f = 0; f + 1 < sg.nh; f += 2) {
+		const int h = sg.hmmbase + f;
+		const int c0 = sg.colbase + f * NC;
+		const float* emA = sm.emit + (size_t)c0 * kEmitRec;
+		const float* emB = emA + (size_t)NC * kEmitRec;
+		const float sM0A = (sm.colrec + (size_t)c0 * kColRec)[F_SM];
+		const float sM0B = (sm.colrec + (size_t)(c0 + NC) * kColRec)[F_SM];
+		const float2* bwqA = bw + (size_t)c0 * a.lmax * kBlock;          // -> (position 1, column 0) of HMM f
+		const float2* bwqB = bwqA + (size_t)NC * a.lmax * kBlock;        //    ... of HMM f + 1
+		float MA[NC], IA[NC], MB[NC], IB[NC];
+		float2 bA[NB], bB[NB];
+#pragma unroll
+		for (int g = 0; g < NC; ++g) { MA[g] = NEG_INF; IA[g] = NEG_INF; MB[g] = NEG_INF; IB[g] = NEG_INF; }
+#pragma unroll
+		for (int g = 0; g < NB; ++g) bA[g] = ld_bw(&bwqA[(size_t)g * kBlock]);
+		float TPA = NEG_INF, TPB = NEG_INF;
+		int pfA = 0xFFFF, plA = 0, pfB = 0xFFFF, plB = 0;
+		float ps1 = first_seg ? 0.0f : ps_arr[0];
+		SeqUp su;
+		su.init(rd, off, a.words);
+		float* csp = cs_arr + kBlock;
+		const float* psp = ps_arr + kBlock;
+		float* pp = post + (size_t)h * kBlock;
+		float cs_n = ld_keep(csp, keep);
+		float ps_n = first_seg ? NEG_INF : ld_keep(psp, keep);
+		const float* qb = sbk + ((size_t)(j + 1) * W + 2) * kBlock;
+		float q_n = (!last_seg) ? ld_keep(qb, keep) : NEG_INF;
+		for (int i = 1; i <= lw; ++i) {
+			const int x = su.get();
+			float cs = cs_n;
+			const float ps0 = ps_n;
+			const float q0 = last_seg ? (i == len ? 0.0f : NEG_INF) : q_n;
+			qb += kBlock;
+			if (!last_seg && i < lw) q_n = ld_keep(qb, keep);
+			// HMM f + 1, this position: in flight while HMM f is computed
+#pragma unroll
+			for (int g = 0; g < NB; ++g) bB[g] = ld_bw(&bwqB[(size_t)g * kBlock]);
+			cs_n = ld_keep(csp + kBlock, keep);
+			if (!first_seg) ps_n = ld_keep(psp + kBlock, keep);
+			const bool act = i <= len;
+			const float eIu = emA[5 + x];
+			// one HMM at this position (the same expressions as fwd_segment<NC, 1>)
+			auto hmm = [&](float (&M)[NC], float (&I)[NC], const float2 (&b)[NB], const float* em, float sM0, float& TP, float& P) {
+				float oldMp, oldIp, newMp, D;
+				{
+					const float nM = ps1 + sM0 + em[x];
+					const float tM = nM + b[0].x - B;
+					TP = LS(TP, tM, tab);
+					P = tM;
+					float v = I[0] + tc;                       // II
+					v = LS(v, M[0] + tb, tab);                 // MI
+					const float nI = v + eIu;
+					P = LS(P, nI + b[0].y - B, tab);
+					oldMp = M[0]; oldIp = I[0]; newMp = nM; D = NEG_INF;
+					M[0] = nM; I[0] = nI;
+				}
+#pragma unroll
+				for (int g = 1; g < NC; ++g) {
+					const int p = g - 1;
+					float2 bg;
+					if (g == NC - 1) bg = make_float2(q0 + 0.0f, NEG_INF);   // the unstored last column, as k_backward computes it
+					else bg = b[g < NB ? g : 0];
+					const float eM = em[g * kEmitRec + x];
+					const float oldMg = M[g], oldIg = I[g];
+					float v = oldMp + ta;                                      // MM of column p
+					v = LS(v, oldIp + td, tab);                                // IM
+					if (p >= 1) v = LS(v, D + (p == NC - 2 ? 0.0f : td), tab);   // DM
+					const float nM = v + eM;
+					P = LS(P, nM + bg.x - B, tab);
+					float nI = NEG_INF;
+					if (g < NC - 1) {
+						float w = oldIg + tc;                                  // II
+						w = LS(w, oldMg + (g == NC - 2 ? tb2 : tb), tab);      // MI
+						nI = w + eIu;
+						P = LS(P, nI + bg.y - B, tab);
+					} else {
+						nI = NEG_INF + eIu;
+					}
+					{
+						float dv = NEG_INF; bool dh = false;
+						if (p <= NC - 3) { dv = newMp + tb; dh = true; }       // MD
+						if (p >= 1 && p <= NC - 3) { const float t = D + tc; dv = dh ? LS(dv, t, tab) : t; }   // DD
+						D = dv;
+					}
+					if (g == NC - 1) cs = LS(cs, nM + 0.0f, tab);              // MSKIP of the last column
+					oldMp = oldMg; oldIp = oldIg; newMp = nM;
+					M[g] = nM; I[g] = nI;
+				}
+				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);
+			};
+			float PA = NEG_INF, PB = NEG_INF;
+			if (act) hmm(MA, IA, bA, emA, sM0A, TPA, PA);
+			// HMM f, next position: in flight while HMM f + 1 is computed
+			if (i < a.lmax) bwqA += bstep;
+#pragma unroll
+			for (int g = 0; g < NB; ++g) bA[g] = ld_bw(&bwqA[(size_t)g * kBlock]);
+			if (act) {
+				hmm(MB, IB, bB, emB, sM0B, TPB, PB);
+				st_keep(csp, cs, keep);
+				if (!(PA < -104.0f)) { plA = i; pfA = min(pfA, i); }
+				if (!(PB < -104.0f)) { plB = i; pfB = min(pfB, i); }
+				if (pfA != 0xFFFF || a.post_store_all) __stcs(pp, PA);
+				if (pfB != 0xFFFF || a.post_store_all) __stcs(pp + kBlock, PB);
+				ps1 = ps0;
+			}
+			if (i < a.lmax) bwqB += bstep;
+			csp += kBlock; psp += kBlock; pp += (size_t)a.H * kBlock;
+		}
+		tp[(size_t)h * kBlock] = TPA;
+		tp[(size_t)(h + 1) * kBlock] = TPB;
+		prange[(size_t)h * kBlock] = ((uint32_t)plA << 16) | (uint32_t)pfA;
+		prange[(size_t)(h + 1) * kBlock] = ((uint32_t)plB << 16) | (uint32_t)pfB;
+	}
+	if (sg.nh & 1) fwd_segment<NC, 1>(a, sm, sg, j, rd, off, len, lw, B, bw, sbk, sf, post, tp, prange, sg.nh - 1);
+}
+#endif
+
 __device__ __forceinline__ float s2p_f(float p)
 {
 	// scaledprob2prob (misc.c:98-105): float argument, double exp, float result
@@ -744,6 +1006,11 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_forward(const KArgs a)
 		const int kind = sg.kind;
 		const int nc = sg.nc;
 #define FWD_CASE(NCV, KINDV) fwd_segment<NCV, KINDV>(a, sm, sg, j, rd, off, len, lw, B, bw, sbk, sf, post, tp, prange)
+#if defined(TDG_FWD_PAIRS) && !defined(TDG_NO_PAIRS)
+#define FWD_PAIR(NCV) do { if (sg.nh >= 2) fwd_pair_std<NCV>(a, sm, sg, j, rd, off, len, lw, B, bw, sbk, sf, post, tp, prange); else FWD_CASE(NCV, 1); } while (0)
+#else
+#define FWD_PAIR(NCV) FWD_CASE(NCV, 1)
+#endif
 #define FWD_LOOP(KINDV)                                                                              \
 	do {                                                                                             \
 		if (a.dyn_cols >= nc) fwd_segment<0, KINDV, true>(a, sm, sg, j, rd, off, len, lw, B, bw, sbk, sf, post, tp, prange);  \
@@ -752,11 +1019,11 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_forward(const KArgs a)
 		if (kind == 1) {
 			switch (nc) {
 				case 3: FWD_CASE(3, 1); break;
-				case 4: FWD_CASE(4, 1); break;
-				case 5: FWD_CASE(5, 1); break;
-				case 6: FWD_CASE(6, 1); break;
-				case 7: FWD_CASE(7, 1); break;
-				case 8: FWD_CASE(8, 1); break;
+				case 4: FWD_PAIR(4); break;
+				case 5: FWD_PAIR(5); break;
+				case 6: FWD_PAIR(6); break;
+				case 7: FWD_PAIR(7); break;
+				case 8: FWD_PAIR(8); break;
 				case 9: FWD_CASE(9, 1); break;
 				case 10: FWD_CASE(10, 1); break;
 				case 11: FWD_CASE(11, 1); break;
@@ -781,6 +1048,7 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_forward(const KArgs a)
 			}
 		}
 #undef FWD_CASE
+#undef FWD_PAIR
 #undef FWD_LOOP
 	}
 	if (!valid) return;
