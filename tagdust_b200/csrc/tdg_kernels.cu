@@ -435,17 +435,22 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// backward, standard-pattern segment, TWO HMMs per position loop (f, f+1).  Same arithmetic and the same order of the
-// silent-state chain as bwd_segment<NC, 1> run on f and then on f+1 -- cs[i] takes f's term, f's skip term, f+1's term,
-// f+1's skip term -- but cs[i] / ps[i] are loaded and stored once per pair (they are 23 % of k_backward's HBM traffic at
-// cfg2, and k_backward is HBM-bound), the sequence word, the insert emission and the loop bookkeeping are shared, and the
-// two recurrences are independent instruction streams.  An odd last HMM goes through bwd_segment.
+// backward, standard-pattern segment, G HMMs per position loop (f .. f+G-1).  Same arithmetic and the same order of the
+// silent-state chain as bwd_segment<NC, 1> run on f, then on f+1, ... -- cs[i] takes f's term, f's skip term, f+1's term,
+// f+1's skip term, ... -- but cs[i] / ps[i] are loaded and stored once per group (they are 23 % of k_backward's HBM
+// traffic at cfg2, and k_backward is HBM-bound), the sequence word, the insert emission and the loop bookkeeping are
+// shared, and the G recurrences are independent instruction streams.  The HMMs that do not fill a group go through
+// bwd_segment.
 // ------------------------------------------------------------------------------------------
 #ifndef TDG_NO_PAIRS
-template <int NC, bool STORE>
-__device__ __forceinline__ void bwd_pair_std(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
-                                             const SeqReader& rd, int off, int len, int lw, int x_term, bool last_seg,
-                                             float2* __restrict__ bw, float* __restrict__ sb)
+#ifndef TDG_BWD_GROUP
+#define TDG_BWD_GROUP 4   // HMMs per position loop for segments of up to 6 columns; measured at cfg2 (6 columns, 49 HMMs), per wave:
+                          // 1: 5.84 ms, 2: 5.03 ms, 3: 4.92-5.01 ms, 4: 4.69-4.76 ms, 5: 4.75-4.85 ms, 6: 4.93 ms, 7: 5.6 ms (spills)
+#endif
+template <int NC, bool STORE, int G>
+__device__ __forceinline__ void bwd_group_std(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
+                                              const SeqReader& rd, int off, int len, int lw, int x_term, bool last_seg,
+                                              float2* __restrict__ bw, float* __restrict__ sb)
 {
 	constexpr int m = NC - 1;
 	constexpr int ncs = NC - 1;
@@ -455,27 +460,29 @@ __device__ __forceinline__ void bwd_pair_std(const KArgs& a, const Smem& sm, con
 	const TabAddr tab = sm.tab;
 	const uint64_t keep = make_keep_policy();
 	const float ta = sg.ta, tb = sg.tb, tb2 = sg.tb2, tc = sg.tc, td = sg.td;
+	const size_t hmm_stride = (size_t)NC * a.lmax * kBlock;   // scratch of one HMM
 
-	for (int f = 0; f + 1 < sg.nh; f += 2) {
+	int f = 0;
+	for (; f + G <= sg.nh; f += G) {
 		const int c0 = sg.colbase + f * NC;
-		const float* emA = sm.emit + (size_t)c0 * kEmitRec;
-		const float* emB = emA + (size_t)NC * kEmitRec;
-		const float sM0A = (sm.colrec + (size_t)c0 * kColRec)[F_SM];
-		const float sM0B = (sm.colrec + (size_t)(c0 + NC) * kColRec)[F_SM];
-		float MA[NC], IA[NC], MB[NC], IB[NC], eMcA[NC], eMcB[NC];
+		const float* em0 = sm.emit + (size_t)c0 * kEmitRec;
+		float M[G][NC], I[G][NC], eMc[G][NC], sM0[G];
 #pragma unroll
-		for (int g = 0; g < NC; ++g) {
-			MA[g] = NEG_INF; IA[g] = NEG_INF; MB[g] = NEG_INF; IB[g] = NEG_INF;
-			eMcA[g] = emA[g * kEmitRec + x_term]; eMcB[g] = emB[g * kEmitRec + x_term];
+		for (int q = 0; q < G; ++q) {
+			sM0[q] = (sm.colrec + (size_t)(c0 + q * NC) * kColRec)[F_SM];
+#pragma unroll
+			for (int g = 0; g < NC; ++g) {
+				M[q][g] = NEG_INF; I[q][g] = NEG_INF;
+				eMc[q][g] = em0[(q * NC + g) * kEmitRec + x_term];
+			}
 		}
-		float eIc = emA[5 + x_term];   // one insert-emission row for the whole segment (checked by the host)
+		float eIc = em0[5 + x_term];   // one insert-emission row for the whole segment (checked by the host)
 		float ps1 = last_seg ? 0.0f : ps_arr[(size_t)(len + 1) * kBlock];
 		SeqDown sd;
 		sd.init(rd, off + lw - 1);
 		float* csp = cs_arr + (size_t)lw * kBlock;
 		const float* psp = ps_arr + (size_t)lw * kBlock;
-		float2* bwpA = bw + ((size_t)c0 * a.lmax + (size_t)(lw - 1) * ncs) * kBlock;
-		float2* bwpB = bwpA + (size_t)NC * a.lmax * kBlock;
+		float2* bwp = bw + ((size_t)c0 * a.lmax + (size_t)(lw - 1) * ncs) * kBlock;   // HMM f; HMM f + q is q * hmm_stride further
 		float cs_n = (lw >= 1) ? ld_keep(csp, keep) : NEG_INF;
 		float ps_n = (!last_seg && lw >= 1) ? ld_keep(psp, keep) : NEG_INF;
 		for (int i = lw; i >= 1; --i) {
@@ -491,26 +498,29 @@ __device__ __forceinline__ void bwd_pair_std(const KArgs& a, const Smem& sm, con
 				if (!last_seg) prefetch_l1(psp - (size_t)kPrefetchDist * kBlock);
 			}
 			if (i <= len) {
-				const float eI0 = emA[5 + x0];
-				// one HMM: columns m .. 0 at this position (the same expressions as bwd_segment<NC, 1>)
-				auto hmm = [&](float (&M)[NC], float (&I)[NC], float (&eMc)[NC], const float* em, float sM0, float2* bwp) {
+				const float eI0 = em0[5 + x0];
+#pragma unroll
+				for (int q = 0; q < G; ++q) {
+					// one HMM: columns m .. 0 at this position (the same expressions as bwd_segment<NC, 1>)
+					const float* em = em0 + (size_t)q * NC * kEmitRec;
+					float2* bq = bwp + (size_t)q * hmm_stride;
 					float eM0[NC];
 #pragma unroll
 					for (int g = 0; g < NC; ++g) eM0[g] = em[g * kEmitRec + x0];
-					float oldMp = M[m];
+					float oldMp = M[q][m];
 					float newMp = ps1 + 0.0f;   // last column: only MSKIP (= +0) is live
 					float D = NEG_INF;
-					M[m] = newMp; I[m] = NEG_INF;
+					M[q][m] = newMp; I[q][m] = NEG_INF;
 #pragma unroll
 					for (int gg = 1; gg < NC; ++gg) {
 						const int g = m - gg, p = g + 1;
-						const float oldMg = M[g];
-						float v = oldMp + eMc[p] + ta;                                             // MM
-						v = LS(v, I[g] + eIc + (g == NC - 2 ? tb2 : tb), tab);                      // MI
+						const float oldMg = M[q][g];
+						float v = oldMp + eMc[q][p] + ta;                                          // MM
+						v = LS(v, I[q][g] + eIc + (g == NC - 2 ? tb2 : tb), tab);                   // MI
 						if (g <= NC - 3) v = LS(v, D + tb, tab);                                    // MD
 						const float nM = v;
-						v = I[g] + tc + eIc;                                                        // II
-						v = LS(v, oldMp + td + eMc[p], tab);                                        // IM
+						v = I[q][g] + tc + eIc;                                                     // II
+						v = LS(v, oldMp + td + eMc[q][p], tab);                                     // IM
 						const float nI = v;
 						{
 							const bool ldd = (g >= 1 && g <= NC - 3), ldm = (g >= 1);
@@ -522,25 +532,23 @@ __device__ __forceinline__ void bwd_pair_std(const KArgs& a, const Smem& sm, con
 							}
 							D = dv;
 						}
-						if (g == 0) cs = LS(cs, nM + sM0 + eM0[0], tab);                            // SM: column 0 only
-						M[g] = nM; I[g] = nI;
+						if (g == 0) cs = LS(cs, nM + sM0[q] + eM0[0], tab);                         // SM: column 0 only
+						M[q][g] = nM; I[q][g] = nI;
 						oldMp = oldMg; newMp = nM;
-						if (STORE) __stcs(&bwp[(size_t)g * kBlock], make_float2(nM, nI));
+						if (STORE) __stcs(&bq[(size_t)g * kBlock], make_float2(nM, nI));
 					}
 					if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);
 #pragma unroll
-					for (int g = 0; g < NC; ++g) eMc[g] = eM0[g];
-				};
-				hmm(MA, IA, eMcA, emA, sM0A, bwpA);
-				hmm(MB, IB, eMcB, emB, sM0B, bwpB);
+					for (int g = 0; g < NC; ++g) eMc[q][g] = eM0[g];
+				}
 				st_keep(csp, cs, keep);
 				eIc = eI0;
 				ps1 = ps0;
 			}
-			csp -= kBlock; psp -= kBlock; bwpA -= (size_t)ncs * kBlock; bwpB -= (size_t)ncs * kBlock;
+			csp -= kBlock; psp -= kBlock; bwp -= (size_t)ncs * kBlock;
 		}
 	}
-	if (sg.nh & 1) bwd_segment<NC, 1, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last_seg, bw, sb, sg.nh - 1);
+	if (f < sg.nh) bwd_segment<NC, 1, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last_seg, bw, sb, f);
 }
 #endif
 
@@ -583,7 +591,11 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a
 		const int nc = sg.nc;
 #define BWD_CASE(NCV, KINDV) bwd_segment<NCV, KINDV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb)
 #ifndef TDG_NO_PAIRS
-#define BWD_PAIR(NCV) do { if (sg.nh >= 2) bwd_pair_std<NCV, STORE>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb); else BWD_CASE(NCV, 1); } while (0)
+// wider segments keep more state per HMM: two HMMs per loop from 7 columns on
+#define BWD_PAIR(NCV) do { constexpr int G_ = (NCV) <= 6 ? TDG_BWD_GROUP : 2; \
+		if (sg.nh >= G_) bwd_group_std<NCV, STORE, G_>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb); \
+		else if (sg.nh >= 2) bwd_group_std<NCV, STORE, 2>(a, sm, sg, j, rd, off, len, lw, x_term, last, bw, sb); \
+		else BWD_CASE(NCV, 1); } while (0)
 #else
 #define BWD_PAIR(NCV) BWD_CASE(NCV, 1)
 #endif

@@ -41,6 +41,15 @@ CASES = {
     "f12_b12_r": dict(segments=["F:NNNNNNNNNNNN", "B:ACGTTGCAACGT,TTGACCATGCAA,GGCATTACCGTA,CATGCATGGTAC,TACGGATCTAGC", "R:N"],
                       barcodes=["ACGTTGCAACGT", "TTGACCATGCAA", "GGCATTACCGTA", "CATGCATGGTAC", "TACGGATCTAGC"], read_len=70,
                       gen=dict(error_rate=0.02, random_frac=0.1, umi_len=12)),
+    # 5-, 7- and 8-nt barcode sets: the grouped backward loop (4 HMMs per position loop up to 6 columns, 2 beyond) with
+    # leftover HMMs that do not fill a group
+    "b5x7_r": dict(segments=["B:ACGTA,TTGAC,GGCAT,CATGC,TACGG,AGTCT,CCATA", "R:N"],
+                   barcodes=["ACGTA", "TTGAC", "GGCAT", "CATGC", "TACGG", "AGTCT", "CCATA"], read_len=50, gen=dict(error_rate=0.02, random_frac=0.1)),
+    "b7x6_r": dict(segments=["B:ACGTACG,TTGACCA,GGCATTA,CATGCAT,TACGGAT,AGTCTGA", "R:N"],
+                   barcodes=["ACGTACG", "TTGACCA", "GGCATTA", "CATGCAT", "TACGGAT", "AGTCTGA"], read_len=50, gen=dict(error_rate=0.02, random_frac=0.1)),
+    "f4_b8x9_r": dict(segments=["F:NNNN", "B:ACGTACGT,TTGACCAT,GGCATTAC,CATGCATG,TACGGATC,AGTCTGAA,CCATAGGC,GTTCAAGT,TGCAGTCA", "R:N"],
+                      barcodes=["ACGTACGT", "TTGACCAT", "GGCATTAC", "CATGCATG", "TACGGATC", "AGTCTGAA", "CCATAGGC", "GTTCAAGT", "TGCAGTCA"],
+                      read_len=60, gen=dict(error_rate=0.02, random_frac=0.1, umi_len=4)),
     # long partial adapters on both ends (column-loop kernel path, generic segments)
     "p18_b_r_p14": dict(segments=["P:AGGGAGGACGATGCGGTC", "B:" + ",".join(TAGS6_ED4[:4]), "R:N", "P:GATCGGAAGAGCAC"], barcodes=TAGS6_ED4[:4],
                         read_len=80, gen=dict(error_rate=0.02, random_frac=0.1, linker5="AGGGAGGACGATGCGGTC", linker3="GATCGGAAGAGCAC"),
