@@ -647,6 +647,8 @@ __global__ void __launch_bounds__(kBlock, 512 / kBlock) k_backward(const KArgs a
 // forward + posterior, one segment.  barcode_hmm.c:4199-4345
 // Mb/Ib of position i+1 (HBM), cs[i+1] and ps[i+1] are loaded one position ahead.
 // ------------------------------------------------------------------------------------------
+template <bool V> struct DeferTag { static constexpr bool value = V; };
+
 template <int NC, int KIND, bool SMS = false>
 __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, const SegInfo sg, int j,
                                             const SeqReader& rd, int off, int len, int lw, float B,
@@ -658,6 +660,17 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 	constexpr int N = Cols<NC, STD>::N;
 	constexpr int UN = NC > 0 ? N : 1;
 	constexpr int NB = NC > 0 ? (STD ? NC - 1 : NC) : 1;  // prefetch registers only on the unrolled paths
+	// Posterior window (unrolled standard segments): P[i][h] is only ever used through exp(), which is exactly 0 below
+	// -104 (post_exp in k_label), and it is a logsum chain of 2 NC - 1 terms.  A logsum is at most its larger operand
+	// + table[0] = ln 2, so if every term is below kPThr = -104 - (2 NC - 2) ln 2 the chain ends below -104 whatever its
+	// bits: the 2 NC - 2 logsums (a third of k_forward's) are skipped and -inf is stored.  Otherwise the chain is run
+	// afterwards on the same operands in the same order.  A NaN term fails the `<` and takes the chain.
+#ifdef TDG_NO_PWIN
+	constexpr bool PW = false;
+#else
+	constexpr bool PW = STD && NC > 0 && !SMS;
+#endif
+	constexpr float kPThr = -104.0f - 0.6932f * (float)(2 * (NC > 0 ? NC : 1) - 2) - 0.01f;
 	const int nc = NC > 0 ? NC : sg.nc;
 	const int ncs = STD ? nc - 1 : nc;  // stored columns (k_backward does not store the last STDU column)
 	const bool last_seg = (j == a.S - 1);
@@ -705,6 +718,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 		// STDU: silent_backward of the next segment at position i+1 (= Mb of the unstored last column)
 		const float* qb = sbk + ((size_t)(j + 1) * W + 2) * kBlock;
 		float q_n = (STD && !last_seg) ? ld_keep(qb, keep) : NEG_INF;
+		bool defer = false;
 		for (int i = 1; i <= lw; ++i) {
 			const int x = su.get();  // seqa[i]
 			float cs = cs_n;
@@ -723,8 +737,14 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 			}
 			cs_n = ld_keep(csp + kBlock, keep);
 			if (!first_seg) ps_n = ld_keep(psp + kBlock, keep);
-			if (i <= len) {
+			// One position of this HMM.  DEFER = the posterior chain is decided after the recurrence (posterior window,
+			// see kPThr); otherwise it is interleaved with the recurrence as the reference writes it.  The deferred chain,
+			// when it has to run, is a bare dependent chain with nothing to overlap, so a warp only defers while all its
+			// reads were outside the window at the previous position (`defer`, warp-uniform).
+			auto position = [&](auto defer_tag) {
+				constexpr bool DEFER = decltype(defer_tag)::value;
 				float P;
+				bool p_small = true;
 				float oldMp, oldIp, newMp, D;
 				const float eIu = STD ? em[5 + x] : 0.0f;  // STDU: one insert emission per position
 				// ---- column 0 (:4218-4266)
@@ -740,6 +760,7 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 					const float tM = nM + b.x - B;
 					TP = LS(TP, tM, tab);
 					P = tM;  // logsum(-inf, tM) == tM
+					if (DEFER) p_small = tM < kPThr;
 					float v;
 					bool have = false;
 					v = NEG_INF;
@@ -748,7 +769,8 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 					if (live_of<STD>(nc, 0, F_MI, lv)) { const float t = M[0] + trv<KIND>(r, sg, nc, 0, F_MI); v = have ? LS(v, t, tab) : t; have = true; }
 					const float nI = v + eI;
 					if (lsi) TP = LS(TP, ps1 + r[F_SI] + eI + b.y - B, tab);
-					P = LS(P, nI + b.y - B, tab);
+					if (DEFER) p_small &= (nI + b.y - B) < kPThr;
+					else P = LS(P, nI + b.y - B, tab);
 					if (live_of<STD>(nc, 0, F_MSKIP, lv)) cs = LS(cs, nM + r[F_MSKIP], tab);
 					if (live_of<STD>(nc, 0, F_ISKIP, lv)) cs = LS(cs, nI + r[F_ISKIP], tab);
 					oldMp = M[0]; oldIp = I[0]; newMp = nM; D = NEG_INF;
@@ -782,14 +804,16 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 						if (live_of<STD>(nc, p, F_DM, lp)) { const float t = D + trv<KIND>(rp, sg, nc, p, F_DM); v = have ? LS(v, t, tab) : t; have = true; }
 						const float nM = v + eM;
 						const bool m_reach = STD ? true : have;
-						if (m_reach) P = LS(P, nM + b.x - B, tab);
+						if (DEFER) p_small &= (nM + b.x - B) < kPThr;
+						else if (m_reach) P = LS(P, nM + b.x - B, tab);
 						// I_forward[g][i]
 						v = NEG_INF; have = false;
 						if (live_of<STD>(nc, g, F_SI, lv)) { v = ps1 + r[F_SI]; have = true; }
 						if (live_of<STD>(nc, g, F_II, lv)) { const float t = oldIg + trv<KIND>(r, sg, nc, g, F_II); v = have ? LS(v, t, tab) : t; have = true; }
 						if (live_of<STD>(nc, g, F_MI, lv)) { const float t = oldMg + trv<KIND>(r, sg, nc, g, F_MI); v = have ? LS(v, t, tab) : t; have = true; }
 						const float nI = v + eI;
-						if (have) P = LS(P, nI + b.y - B, tab);
+						if (DEFER) { if (have) p_small &= (nI + b.y - B) < kPThr; }
+						else if (have) P = LS(P, nI + b.y - B, tab);
 						// D_forward[g][i]
 						{
 							float dv = NEG_INF; bool dh = false;
@@ -805,6 +829,20 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				}
 				if (skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // (:4341)
 				st_keep(csp, cs, keep);
+				if (DEFER) {
+					if (p_small) P = NEG_INF;
+					else {
+						// the posterior chain (:4230-4330) on the states just computed, in the reference's order
+						P = M[0] + bc[0].x - B;
+						P = LS(P, I[0] + bc[0].y - B, tab);
+#pragma unroll
+						for (int g = 1; g < N; ++g) {
+							const float bx = (g == NC - 1) ? q0 + 0.0f : bc[g < NB ? g : 0].x;
+							P = LS(P, M[g] + bx - B, tab);
+							if (g < NC - 1) P = LS(P, I[g] + bc[g < NB ? g : 0].y - B, tab);
+						}
+					}
+				}
 				// [pfirst, plast]: the window outside which exp(P) is exactly 0 (k_label skips HMMs without predecessors there)
 				if (!(P < -104.0f)) { plast = i; pfirst = min(pfirst, i); }
 				// k_label loads every posterior (no per-HMM window test), so all of them are stored.  The predicate is always
@@ -817,7 +855,14 @@ __device__ __forceinline__ void fwd_segment(const KArgs& a, const Smem& sm, cons
 				if (pfirst != 0xFFFF || a.post_store_all) __stcs(pp, P);
 #endif
 				ps1 = ps0;
+				return P < -104.0f;
+			};
+			bool outside = true;   // this read is outside the posterior window at this position (or has ended)
+			if (i <= len) {
+				if (PW && defer) outside = position(DeferTag<PW>{});
+				else outside = position(DeferTag<false>{});
 			}
+			if (PW) defer = __all_sync(0xffffffffu, outside) != 0;
 			csp += kBlock; psp += kBlock; pp += (size_t)a.H * kBlock;
 		}
 		tp[(size_t)h * kBlock] = TP;
