@@ -60,6 +60,8 @@ struct SegInfo {
 	int32_t skip_live; // skip != -inf
 	int32_t kind;      // code path: 0 generic (runtime live masks), 1 STDU (standard pattern, uniform scalars)
 	float   ta, tb, tb2, tc, td;  // STDU transition scalars (see trv<> in tdg_kernels.cu)
+	int32_t use_win;   // 1: k_backward records the largest Mb/Ib of the segment per position (KArgs.mbmax) and k_forward
+	                   //    skips the Mb/Ib loads and the posterior chain of cells that provably exp() to 0 (unrolled STDU only)
 };
 
 // Everything a kernel needs that is not in the model blob (passed by value).
@@ -87,6 +89,7 @@ struct KArgs {
 	float2* bw;                // [cta][C*lmax][kBlock]  (Mb, Ib)
 	float*  sb;                // [cta][S*(lmax+2)][kBlock] silent_backward
 	float*  sf;                // [cta][S*(lmax+2)][kBlock] silent_forward
+	float*  mbmax;             // [cta][S*(lmax+2)][kBlock] max over the segment's HMMs and columns of Mb / Ib at a position
 	float*  post;              // [cta][lmax*H][kBlock] posterior matrix rows 1..L
 	float*  tp;                // [cta][H][kBlock] total_prob
 	uint32_t* prange;          // [cta][H][kBlock] (last<<16)|first position with posterior >= -104

@@ -287,7 +287,7 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 		SegInfo& g = hm.seg[s];
 		g.nh = d->seg_num_hmms[s]; g.nc = d->seg_num_cols[s];
 		if (g.nh < 1 || g.nc < 1 || g.nc > kMaxSegCols) { snprintf(buf, sizeof buf, "segment %d: %d HMMs x %d columns unsupported (columns 1..%d)", s, g.nh, g.nc, kMaxSegCols); err = buf; return TDG_EINVAL; }
-		g.colbase = cb; g.hmmbase = hb; g.skip = d->seg_skip[s]; g.skip_live = !is_ninf(g.skip); g.kind = 0;
+		g.colbase = cb; g.hmmbase = hb; g.skip = d->seg_skip[s]; g.skip_live = !is_ninf(g.skip); g.kind = 0; g.use_win = 0;
 		cb += g.nh * g.nc; hb += g.nh;
 	}
 	if (cb != C || hb != H) { err = "total_columns / total_hmms inconsistent with the segment tables"; return TDG_EINVAL; }
@@ -341,6 +341,7 @@ static int derive_model(const tdg_model_desc* d, HostModel& hm, std::string& err
 				if (col == g.nc - 2 && !same(r[F_DM], 0.0f)) ok = false;
 			}
 		if (ok) { g.kind = 1; g.ta = ta; g.tb = tb; g.tb2 = tb2; g.tc = tc; g.td = td; hm.std_segments++; }
+		g.use_win = (ok && g.nc >= 3 && g.nc <= kMaxStdCols && !getenv("TDG_NO_WIN")) ? 1 : 0;
 	}
 	for (int s = 0; s < S; s++) {
 		const SegInfo& g = hm.seg[s];
@@ -538,7 +539,7 @@ extern "C" int tdg_model_create(tdg_context* ctx, const tdg_model_desc* desc, in
 	if (getenv("TDG_MODEL_IN_GLOBAL")) m->model_in_smem = 0;  // tests: force the global-memory tables
 	const size_t W = (size_t)max_len + 2;
 	m->slot_bytes_bwd = (size_t)hm.S * W * 4;
-	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
+	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 3 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
 	                     (size_t)max_len * hm.H;
 	m->dev.resize(ctx->devs.size());
 	for (size_t k = 0; k < ctx->devs.size(); k++) {
@@ -896,7 +897,7 @@ extern "C" int tdg_model_set_max_len(tdg_model* m, int max_len)
 	const size_t W = (size_t)max_len + 2;
 	m->max_len = max_len;
 	m->slot_bytes_bwd = (size_t)hm.S * W * 4;
-	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 2 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
+	m->slot_bytes_full = (size_t)hm.C * max_len * 8 + 3 * (size_t)hm.S * W * 4 + (size_t)max_len * hm.H * 4 + (size_t)hm.H * 8 +
 	                     (size_t)max_len * hm.H;
 	return TDG_OK;
 }
@@ -996,6 +997,7 @@ static void carve_scratch(KArgs& a, const tdg_model* m, const DeviceCtx& d, bool
 	a.sb = (float*)take(slots * hm.S * W * 4);
 	if (full) {
 		a.sf = (float*)take(slots * hm.S * W * 4);
+		a.mbmax = (float*)take(slots * hm.S * W * 4);
 		a.tp = (float*)take(slots * hm.H * 4);
 		a.prange = (uint32_t*)take(slots * hm.H * 4);
 		a.post = (float*)take(slots * (size_t)m->max_len * hm.H * 4);

@@ -266,6 +266,12 @@ __device__ __forceinline__ float trv(const float* r, const SegInfo& sg, int nc, 
 	return r[field];
 }
 
+// this thread's lane of the per-position maximum of Mb / Ib (same geometry as silent_backward)
+__device__ __forceinline__ float* a_mbmax_lane(const KArgs& a)
+{
+	return a.mbmax + (size_t)blockIdx.x * ((size_t)a.S * (size_t)(a.lmax + 2)) * kBlock + threadIdx.x;
+}
+
 // ------------------------------------------------------------------------------------------
 // backward, one segment (all HMMs f, all positions i).  barcode_hmm.c:3496-3607
 // The silent-state values of the next iteration (cs[i-1], ps[i-1]) are loaded one position
@@ -290,6 +296,8 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 	const float* ps_arr = sb + ((size_t)(j + 1) * W) * kBlock;
 	const TabAddr tab = sm.tab;
 	const uint64_t keep = make_keep_policy();
+	const bool win = STORE && STD && NC > 0 && !SMS && sg.use_win;   // see bwd_group_std
+	float* mb_arr = win ? a_mbmax_lane(a) + ((size_t)j * W) * kBlock : nullptr;
 
 	for (int f = f_begin; f < sg.nh; ++f) {
 		const int c0 = sg.colbase + f * nc;
@@ -344,6 +352,8 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 				if (!last_seg) prefetch_l1(psp - (size_t)kPrefetchDist * kBlock);
 			}
 			if (i <= len) {
+				float* mbp = win ? mb_arr + (size_t)i * kBlock : nullptr;
+				float gmax = (win && f > 0) ? ld_keep(mbp, keep) : NEG_INF;
 				float eM0[SMS ? 1 : N];
 				float eI0[(STD || SMS) ? 1 : N];
 				if (!SMS) {
@@ -413,10 +423,12 @@ __device__ __forceinline__ void bwd_segment(const KArgs& a, const Smem& sm, cons
 						M[g] = nM; I[g] = nI;
 						oldMp = oldMg; newMp = nM;
 						if (STORE) __stcs(&bwp[(size_t)g * kBlock], make_float2(nM, nI));
+						if (win) gmax = fmaxf(gmax, fmaxf(nM, nI));
 					}
 				}
 				if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);  // once per HMM f (:3604)
 				st_keep(csp, cs, keep);
+				if (win) st_keep(mbp, gmax, keep);
 #pragma unroll UN
 				for (int g = 0; g < (NC > 0 ? N : nc); ++g) {
 					if (!SMS && g < nc) { eMc[SMS ? 0 : g] = eM0[SMS ? 0 : g]; if (!STD) eIc[(STD || SMS) ? 0 : g] = eI0[(STD || SMS) ? 0 : g]; }
@@ -461,6 +473,8 @@ __device__ __forceinline__ void bwd_group_std(const KArgs& a, const Smem& sm, co
 	const uint64_t keep = make_keep_policy();
 	const float ta = sg.ta, tb = sg.tb, tb2 = sg.tb2, tc = sg.tc, td = sg.td;
 	const size_t hmm_stride = (size_t)NC * a.lmax * kBlock;   // scratch of one HMM
+	const bool win = STORE && sg.use_win;                     // record max(Mb, Ib) of the segment per position for k_forward
+	float* mb_arr = win ? a_mbmax_lane(a) + ((size_t)j * W) * kBlock : nullptr;
 
 	int f = 0;
 	for (; f + G <= sg.nh; f += G) {
@@ -499,6 +513,8 @@ __device__ __forceinline__ void bwd_group_std(const KArgs& a, const Smem& sm, co
 			}
 			if (i <= len) {
 				const float eI0 = em0[5 + x0];
+				float* mbp = win ? mb_arr + (size_t)i * kBlock : nullptr;
+				float gmax = (win && f > 0) ? ld_keep(mbp, keep) : NEG_INF;   // what the HMMs before this group recorded
 #pragma unroll
 				for (int q = 0; q < G; ++q) {
 					// one HMM: columns m .. 0 at this position (the same expressions as bwd_segment<NC, 1>)
@@ -536,12 +552,14 @@ __device__ __forceinline__ void bwd_group_std(const KArgs& a, const Smem& sm, co
 						M[q][g] = nM; I[q][g] = nI;
 						oldMp = oldMg; newMp = nM;
 						if (STORE) __stcs(&bq[(size_t)g * kBlock], make_float2(nM, nI));
+						if (win) gmax = fmaxf(gmax, fmaxf(nM, nI));
 					}
 					if (sg.skip_live) cs = LS(cs, ps0 + sg.skip, tab);
 #pragma unroll
 					for (int g = 0; g < NC; ++g) eMc[q][g] = eM0[g];
 				}
 				st_keep(csp, cs, keep);
+				if (win) st_keep(mbp, gmax, keep);
 				eIc = eI0;
 				ps1 = ps0;
 			}
