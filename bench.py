@@ -589,7 +589,9 @@ def run_gpu_arm(args):
                      "peak_source": f"148 SM x 128 FP32 lanes x sm_max_mhz, {pk_src}",
                      "note": "frac = LIVE FP32-pipe ops (logsums and adds the kernel executes; a logsum = 9 ops as in SURVEY 8d) "
                              "/ duration / lane peak; frac_algorithmic counts SURVEY 8d's 8+10 logsums per (column, position) "
-                             "including the log(0) terms that are never evaluated, so it can exceed 1; T lane-ops/s in the TFLOP/s unit"},
+                             "including the log(0) terms that are never evaluated, so it can exceed 1; the posterior window of k_forward "
+                             "skips a data-dependent share of the live posterior logsums at run time (they exp() to exactly 0), "
+                             "which this count keeps; T lane-ops/s in the TFLOP/s unit"},
         "roofline_whole_path": {"achieved": value / world * READ_LEN * (live_pos["k_backward"] + live_pos["k_forward"]) / 1e12,
                                 "achieved_algorithmic": value / world * READ_LEN * C * (OPS_PER_COLPOS_BWD + OPS_PER_COLPOS_FWD) / 1e12,
                                 "peak": fp32_peak, "unit": "TFLOP/s"},
