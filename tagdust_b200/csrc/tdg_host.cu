@@ -23,6 +23,7 @@
 #include "../../include/tagdust_b200.h"
 #include "../../include/tagdust_b200_stream.h"
 #include "tdg_device.h"
+#include "tdg_pack.h"
 
 using namespace tdg;
 
@@ -1473,43 +1474,20 @@ void batch_release(tdg_batch* b)
 	if (victim) tdg_batch_destroy(victim);
 }
 
-// Packs reads straight from the characters of a FASTQ text (no intermediate code array): code_of[] is the reference's
-// nuc_code table (nuc_code.c:46-74), text + seq_pos[i] the first base of read i.  The code behind the last base is 0.
-static inline void pack_read_text(tdg_batch* b, int r, const uint8_t* s, int len, const uint8_t* code_of)
+// The streaming layer packs reads straight from the characters of a FASTQ text into the pinned staging arrays
+// (tdg_pack.h: pack_text_read, on its own worker pool, in the same pass that measures the lines): this hands out the
+// arrays for the next n reads of the batch, batch_text_commit makes them part of it.
+int batch_text_target(tdg_batch* b, int n, TextTarget* t)
 {
-	uint32_t* base = b->h_seq + ((size_t)(r >> 5) * b->words) * 32 + (r & 31);
-	int pos = 0;
-	for (int w = 0; w < b->words; w++) {
-		uint32_t v = 0;
-		if (pos + 8 <= len) {
-			for (int k = 0; k < 8; k++) v |= (uint32_t)code_of[s[pos + k]] << (4 * k);
-			pos += 8;
-		} else {
-			for (int k = 0; k < 8 && pos < len; k++, pos++) v |= (uint32_t)(code_of[s[pos]] & 0xF) << (4 * k);
-			pos = len + 8;   // the terminator (code 0) and everything behind it are zero bits
-		}
-		base[(size_t)w * 32] = v;
-	}
-	b->h_len[r] = len;
+	if (!b || !t) return fail(TDG_EINVAL, "NULL argument");
+	if (n < 0 || b->n + n > b->max_reads) return fail(TDG_EINVAL, "batch overflow: %d + %d > %d", b->n, n, b->max_reads);
+	t->seq = b->h_seq; t->len = b->h_len; t->words = b->words; t->max_len = b->max_len; t->first = b->n;
+	return TDG_OK;
 }
 
-int batch_append_text(tdg_batch* b, int n, const char* text, const uint64_t* seq_pos, const int32_t* len, const uint8_t* code_of, int threads)
+int batch_text_commit(tdg_batch* b, int n)
 {
-	if (!b || !text || !seq_pos || !len || !code_of) return fail(TDG_EINVAL, "NULL argument");
-	if (n < 0 || b->n + n > b->max_reads) return fail(TDG_EINVAL, "batch overflow: %d + %d > %d", b->n, n, b->max_reads);
-	for (int i = 0; i < n; i++)
-		if (len[i] < 0 || len[i] > b->max_len) return fail(TDG_EINVAL, "read %d: length %d exceeds batch max_len %d", i, len[i], b->max_len);
-	const int first = b->n;
-	const int T = std::max(1, std::min(threads, n / 4096));
-	auto work = [&](int lo, int hi) { for (int i = lo; i < hi; i++) pack_read_text(b, first + i, (const uint8_t*)text + seq_pos[i], len[i], code_of); };
-	if (T <= 1) work(0, n);
-	else {
-		std::vector<std::thread> th;
-		const int per = (n + T - 1) / T;
-		for (int t = 1; t < T; t++) th.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
-		work(0, std::min(n, per));
-		for (auto& x : th) x.join();
-	}
+	if (!b || n < 0 || b->n + n > b->max_reads) return fail(TDG_EINVAL, "batch_text_commit: bad count");
 	b->n += n;
 	return TDG_OK;
 }

@@ -31,13 +31,19 @@
 #include <cstring>
 #include <deque>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include "../../include/tagdust_b200_stream.h"
 #include "tdg_device.h"
+#include "tdg_pack.h"
 
 namespace tdg {
 // tdg_host.cu
@@ -46,7 +52,8 @@ int batch_acquire(tdg_context* ctx, int max_reads, int max_len, tdg_batch** out)
 void batch_release(tdg_batch* b);
 int batch_prepare(tdg_batch* b, const tdg_model* m, bool host_labels);
 int scratch_prepare(tdg_context* ctx, tdg_model* m);
-int batch_append_text(tdg_batch* b, int n, const char* text, const uint64_t* seq_pos, const int32_t* len, const uint8_t* code_of, int threads);
+int batch_text_target(tdg_batch* b, int n, TextTarget* t);
+int batch_text_commit(tdg_batch* b, int n);
 }
 
 namespace {
@@ -68,15 +75,86 @@ int failf(int code, const char* fmt, ...)
 	return tdg::set_last_error(code, buf);
 }
 
-// fn(begin, end, thread_index) over [0, n) on up to `threads` threads (the caller is one of them)
+// One set of worker threads for all the stages of a streaming job.  Every stage thread hands its loops to the same
+// workers part by part, so the stages together never run more threads than the job was given (three stages that each
+// start `threads` threads of their own oversubscribe the cores three times, and every loop then waits for its slowest,
+// descheduled thread), and no loop pays for thread creation.
+class WorkerPool {
+public:
+	explicit WorkerPool(int workers)
+	{
+		for (int k = 0; k < workers; k++) th_.emplace_back([this] { work(); });
+	}
+	~WorkerPool()
+	{
+		{ std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+		cv_work_.notify_all();
+		for (auto& t : th_) t.join();
+	}
+	// fn(part) for every part in [0, parts), in any order, on the workers and on the caller; returns when all are done
+	void run(int parts, const std::function<void(int)>& fn)
+	{
+		if (parts <= 0) return;
+		Job j;
+		j.fn = &fn; j.parts = parts;
+		std::unique_lock<std::mutex> l(mu_);
+		jobs_.push_back(&j);
+		if (parts > 1) cv_work_.notify_all();
+		while (j.next < j.parts) {
+			const int p = take(&j);
+			l.unlock();
+			fn(p);
+			l.lock();
+			j.done++;
+		}
+		cv_done_.wait(l, [&] { return j.done == j.parts; });
+	}
+private:
+	struct Job { const std::function<void(int)>* fn = nullptr; int parts = 0, next = 0, done = 0; };
+	int take(Job* j)  // mu_ held, j->next < j->parts
+	{
+		const int p = j->next++;
+		if (j->next == j->parts) jobs_.erase(std::find(jobs_.begin(), jobs_.end(), j));
+		return p;
+	}
+	void work()
+	{
+		std::unique_lock<std::mutex> l(mu_);
+		for (;;) {
+			cv_work_.wait(l, [&] { return stop_ || !jobs_.empty(); });
+			if (jobs_.empty()) return;  // stop_
+			Job* j = jobs_[rr_++ % jobs_.size()];   // the stages take turns
+			const int p = take(j);
+			l.unlock();
+			(*j->fn)(p);
+			l.lock();
+			if (++j->done == j->parts) cv_done_.notify_all();
+		}
+	}
+	std::mutex mu_;
+	std::condition_variable cv_work_, cv_done_;
+	std::vector<Job*> jobs_;   // jobs with parts left to hand out
+	std::vector<std::thread> th_;
+	size_t rr_ = 0;
+	bool stop_ = false;
+};
+thread_local WorkerPool* tl_pool = nullptr;   // set by the stage threads of tdg_demux_run
+
+// fn(begin, end, part_index) over [0, n) in up to `threads` equal parts (part_index < threads): on the streaming job's
+// worker pool when the calling thread belongs to one, else on threads of its own (the caller is one of them)
 template <class F>
 void parallel_for(int threads, size_t n, size_t grain, F fn)
 {
 	int T = std::max(1, threads);
 	if (grain > 0) T = (int)std::min<size_t>(T, std::max<size_t>(1, n / grain));
 	if (T <= 1) { fn((size_t)0, n, 0); return; }
-	std::vector<std::thread> th;
 	const size_t per = (n + T - 1) / T;
+	if (tl_pool) {
+		const std::function<void(int)> part = [&](int t) { fn(std::min(n, per * (size_t)t), std::min(n, per * (size_t)(t + 1)), t); };
+		tl_pool->run(T, part);
+		return;
+	}
+	std::vector<std::thread> th;
 	for (int t = 1; t < T; t++) {
 		const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
 		th.emplace_back([=] { fn(b, e, t); });
@@ -105,6 +183,18 @@ const NucTable kNuc;
 inline uint32_t ctl_span(const uint8_t* s, uint32_t n)
 {
 	uint32_t i = 0;
+#if defined(__SSE2__)
+	{
+		const __m128i k1f = _mm_set1_epi8(0x1F), k7f = _mm_set1_epi8(0x7F);
+		while (i + 16 <= n) {
+			const __m128i x = _mm_loadu_si128((const __m128i*)(s + i));
+			const __m128i c = _mm_or_si128(_mm_cmpeq_epi8(_mm_min_epu8(x, k1f), x), _mm_cmpeq_epi8(x, k7f));   // <= 0x1F, == 0x7F
+			const int m = _mm_movemask_epi8(c);
+			if (m) return i + (uint32_t)__builtin_ctz((unsigned)m);
+			i += 16;
+		}
+	}
+#endif
 	const uint64_t k7f = 0x7F7F7F7F7F7F7F7FULL, k80 = 0x8080808080808080ULL, k01 = 0x0101010101010101ULL;
 	while (i + 8 <= n) {
 		uint64_t x;
@@ -462,18 +552,32 @@ static int split_lines_parallel(tdg_fastq* f, int max_reads, int threads, Parsed
 				sp.end_state = c;
 			}
 		});
-		// stitch
+		// stitch: the order of the stretches and the state each one starts in are settled one after the other; the line
+		// tables themselves (48 bytes per entry) are copied into place by all workers afterwards, and the lines a stretch
+		// found for the entry the stretch before it ended in (orphans) are applied to that entry last
 		const size_t recs_before = pc.recs.size();
+		struct Move { size_t at; const ParsedChunk::Rec* src; size_t n; };
+		struct Late { size_t at; const SplitOut* o; int q; };
+		std::vector<Move> moves;
+		std::vector<Late> late;
+		size_t total = pc.recs.size();
 		auto merge = [&](SplitOut& o) -> bool {
 			if (o.dup || o.overflow) return false;
 			for (int q = 0; q < o.n_orphan; q++)
-				if (!pc.recs.empty()) SplitOut::assign(pc.recs.back(), o.orphan[q].kind, o.orphan[q].pos, o.orphan[q].n, o.orphan[q].next, fasta, dup);
-			if (o.recs.size()) {
-				const size_t at = pc.recs.size();
-				pc.recs.resize(at + o.recs.size());
-				memcpy(pc.recs.data() + at, o.recs.data(), o.recs.size() * sizeof(ParsedChunk::Rec));
-			}
+				if (total) late.push_back({total - 1, &o, q});
+			if (o.recs.size()) { moves.push_back({total, o.recs.data(), o.recs.size()}); total += o.recs.size(); }
 			return true;
+		};
+		auto settle = [&] {
+			pc.recs.resize(total);
+			ParsedChunk::Rec* dst = pc.recs.data();
+			parallel_for(T, moves.size(), 0, [&](size_t mb, size_t me, int) {
+				for (size_t m = mb; m < me; m++) memcpy(dst + moves[m].at, moves[m].src, moves[m].n * sizeof(ParsedChunk::Rec));
+			});
+			for (const Late& l : late) {
+				const auto& x = l.o->orphan[l.q];
+				SplitOut::assign(dst[l.at], x.kind, x.pos, x.n, x.next, fasta, dup);
+			}
 		};
 		for (int k = 0; k < P; k++) {
 			SplitPart& sp = parts[k];
@@ -494,6 +598,7 @@ static int split_lines_parallel(tdg_fastq* f, int max_reads, int threads, Parsed
 			if (!merge(sp.pre[q]) || !merge(sp.rest)) return 0;
 			st = sp.end_state;
 		}
+		settle();
 		if (dup) return 0;
 		if (pc.recs.size() > recs_before) f->bytes_per_entry = (double)wbytes / (double)(pc.recs.size() - recs_before);
 		pos = wend;
@@ -593,9 +698,10 @@ static int convert_chunk(ParsedChunk& pc, int threads)
 }
 
 // Lean conversion (tdg_demux_run): lengths and validation only.  The 4-bit packing reads the sequence characters from
-// the text (tdg::batch_append_text), the writer formats names / bases / qualities from the text: the intermediate arrays
+// the text (the per-read hook of this pass, tdg::pack_text_read), the writer formats names / bases / qualities from the text: the intermediate arrays
 // of convert_chunk (about 1.5 x the input in writes, and as much again in reads by the writer) are never made.
-static int lean_chunk(ParsedChunk& pc, int threads)
+template <class Hook>   // hook(r, first base, length): called once per read by the thread that measured it
+static int lean_chunk(ParsedChunk& pc, int threads, Hook hook)
 {
 	const int n = pc.n;
 	if (n == 0) return TDG_OK;
@@ -617,6 +723,7 @@ static int lean_chunk(ParsedChunk& pc, int threads)
 			pc.seq_pos[r] = R.seq;
 			pc.len[r] = (int32_t)i;
 			if ((int)i > mx) mx = (int)i;
+			hook(r, (const uint8_t*)base + R.seq, (int)i);
 			pc.qual_pos[r] = R.qual;
 			if (!fasta && ctl_span((const uint8_t*)base + R.qual, R.qual_n) != i) { int exp = -1; bad.compare_exchange_strong(exp, (int)r); }
 		}
@@ -752,6 +859,25 @@ inline char* put_int(char* p, int v)
 	do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
 	while (k) *p++ = tmp[--k];
 	return p;
+}
+
+// print_all's characters (io.c:757: "ACGTNN"[code]) of n input characters: upper-case A, C, G, T and N stand for themselves
+// -- sixteen at a time where a block holds nothing else -- everything else goes through the table.
+inline char* put_bases(char* p, const uint8_t* s, int n)
+{
+	int q = 0;
+#if defined(__SSE2__)
+	const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T'), cN = _mm_set1_epi8('N');
+	for (; q + 16 <= n; q += 16) {
+		const __m128i x = _mm_loadu_si128((const __m128i*)(s + q));
+		const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(x, cA), _mm_cmpeq_epi8(x, cC)), _mm_or_si128(_mm_cmpeq_epi8(x, cG), _mm_cmpeq_epi8(x, cT))),
+		                                _mm_cmpeq_epi8(x, cN));
+		if (_mm_movemask_epi8(ok) == 0xFFFF) _mm_storeu_si128((__m128i*)(p + q), x);
+		else for (int k = 0; k < 16; k++) p[q + k] = kNuc.out[s[q + k]];
+	}
+#endif
+	for (; q < n; q++) p[q] = kNuc.out[s[q]];
+	return p + n;
 }
 
 // dust_sequences (barcode_hmm.c:2407-2467) on one read; `seq` is 0-terminated like ri->seq
@@ -966,9 +1092,14 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	};
 	std::atomic<int64_t> long_events{0};
 	double sec_split = 0, sec_parse = 0, sec_gpu = 0, sec_write = 0;
+	// the workers all three host stages share; a stage thread works on its own loops too while it waits for them
+	std::unique_ptr<WorkerPool> pool;
+	if (threads > 1) pool.reset(new WorkerPool(threads));
+	WorkerPool* const poolp = pool.get();
 
 	// ---- stage 1a: line splitting (sequential per file)
 	std::thread t_split([&] {
+		tl_pool = poolp;
 		try {
 		std::vector<SplitPart> split_scratch;
 		for (;;) {
@@ -1000,6 +1131,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 
 	// ---- stage 1b: conversion + packing on the worker pool
 	std::thread t_parse([&] {
+		tl_pool = poolp;
 		try {
 		std::vector<int> run_max(NI);
 		for (int i = 0; i < NI; i++) run_max[i] = job->inputs[i].max_seq_len;
@@ -1012,32 +1144,53 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 			const double t0 = now_s();
 			bool ok = true;
 			if (!s.last) {
-				for (int i = 0; i < NI && ok; i++)
-					if (lean_chunk(s.pc[i], threads) != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; }
 				for (int i = 0; i < NI && ok; i++) {
 					ParsedChunk& pc = s.pc[i];
+					tdg_model* m = job->inputs[i].model;
+					const bool to_gpu = m || job->refset;   // model-less files reach the GPU only for the artifact filter
+					// the reads are packed into the staging batch by the pass that measures them (the bases are in cache then);
+					// a chunk with a read longer than the batch was made for is packed again into a longer batch
+					tdg::TextTarget tt;
+					auto fresh_batch = [&](int min_len) -> bool {
+						if (!s.batch[i] || s.batch_reads[i] < pc.n || s.batch_len[i] < min_len) {
+							if (s.batch[i]) tdg_batch_destroy(s.batch[i]);
+							s.batch[i] = nullptr;
+							s.batch_reads[i] = std::max(s.batch_reads[i], std::max(pc.n, std::min(chunk_reads, 1 << 24)));
+							s.batch_len[i] = std::max(s.batch_len[i], min_len);
+							if (tdg::batch_acquire(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); return false; }
+						}
+						tdg_batch_clear(s.batch[i]);
+						if (tdg::batch_text_target(s.batch[i], pc.n, &tt) != TDG_OK) { sh.fail(TDG_EINVAL, tdg_last_error()); return false; }
+						return true;
+					};
+					if (to_gpu && !fresh_batch(s.batch_len[i])) { ok = false; break; }
+					const uint8_t* code_of = kNuc.code;
+					const bool nuc_std = tdg::is_nuc_code_table(kNuc.code);
+					int rc;
+					if (to_gpu) rc = lean_chunk(pc, threads, [&tt, code_of, nuc_std](size_t r, const uint8_t* seq, int len) {
+						if (len <= tt.max_len) tdg::pack_text_read(tt, (int)r, seq, len, code_of, nuc_std);
+					});
+					else rc = lean_chunk(pc, threads, [](size_t, const uint8_t*, int) {});
+					if (rc != TDG_OK) { sh.fail(TDG_EFORMAT, tdg_last_error()); ok = false; break; }
+					tr("lengths", k, t0);
 					// barcode_hmm.c:293-309: every read at least as long as the running maximum rebuilds the model
 					int64_t ev = 0;
 					int mx = run_max[i];
 					for (int r = 0; r < pc.n; r++) if (pc.len[r] >= mx) { mx = pc.len[r]; ev++; }
 					run_max[i] = mx;
 					long_events += ev;
-					tdg_model* m = job->inputs[i].model;
-					if (!m && !job->refset) continue;   // model-less files reach the GPU only for the artifact filter
+					if (!to_gpu) continue;
 					int need = pc.max_len;
 					if (job->matchstart != -1 || job->matchend != -1) need = std::max(need, job->matchend);
 					if (m && need > tdg_model_max_len(m)) tdg_model_set_max_len(m, need + 10);
-					if (!s.batch[i] || s.batch_reads[i] < pc.n || s.batch_len[i] < pc.max_len) {
-						if (s.batch[i]) tdg_batch_destroy(s.batch[i]);
-						s.batch[i] = nullptr;
-						s.batch_reads[i] = std::max(s.batch_reads[i], std::max(pc.n, std::min(chunk_reads, 1 << 24)));
-						s.batch_len[i] = std::max(s.batch_len[i], pc.max_len);
-						if (tdg::batch_acquire(ctx, s.batch_reads[i], s.batch_len[i], &s.batch[i]) != TDG_OK) { sh.fail(TDG_ECUDA, tdg_last_error()); ok = false; break; }
+					if (pc.max_len > tt.max_len) {
+						if (!fresh_batch(pc.max_len)) { ok = false; break; }
+						const char* text = pc.text;
+						parallel_for(threads, (size_t)pc.n, 2048, [&](size_t b, size_t e, int) {
+							for (size_t r = b; r < e; r++) tdg::pack_text_read(tt, (int)r, (const uint8_t*)text + pc.seq_pos[r], pc.len[r], code_of, nuc_std);
+						});
 					}
-					tdg_batch_clear(s.batch[i]);
-					if (tdg::batch_append_text(s.batch[i], pc.n, pc.text, pc.seq_pos.data(), pc.len.data(), kNuc.code, threads) != TDG_OK) {
-						sh.fail(TDG_EINVAL, tdg_last_error()); ok = false;
-					}
+					if (tdg::batch_text_commit(s.batch[i], pc.n) != TDG_OK) { sh.fail(TDG_EINVAL, tdg_last_error()); ok = false; break; }
 				}
 			}
 			sec_parse += now_s() - t0;
@@ -1097,6 +1250,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 
 	// ---- stage 3: post-process + write
 	std::thread t_write([&] {
+		tl_pool = poolp;
 		try {
 		std::vector<std::vector<OutBuf>> ob((size_t)threads, std::vector<OutBuf>((size_t)num_outfiles));
 		std::vector<std::vector<int64_t>> tally((size_t)threads, std::vector<int64_t>(8, 0));
@@ -1168,10 +1322,11 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 							const int s1 = std::min(len, s0 + sl);
 							int g = s0;
 							while (g < s1) {
-								while (g < s1 && kNuc.code[seq[g]] >= 5) g++;
-								int h = g;
-								while (h < s1 && kNuc.code[seq[h]] < 5) h++;
-								if (h == g) break;
+								// the only character with a code >= 5 is '.' (nuc_code.c:52)
+								while (g < s1 && seq[g] == '.') g++;
+								if (g == s1) break;
+								const void* dot = memchr(seq + g, '.', (size_t)(s1 - g));
+								const int h = dot ? (int)((const uint8_t*)dot - seq) : s1;
 								const bool more = h < len;  // something follows the run: the next run goes to the next READ file
 								if (f >= 0 && f < num_outfiles && files[f]) {
 									const int run = h - g;
@@ -1192,7 +1347,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 									memcpy(p, ";RQ:", 4); p += 4;
 									p += tdg_format_rq(mq[i], p);
 									*p++ = '\n';
-									for (int q = g; q < h; q++) *p++ = kNuc.out[seq[q]];
+									p = put_bases(p, seq + g, run);
 									*p++ = '\n'; *p++ = '+'; *p++ = '\n';
 									if (ql) { memcpy(p, ql + g, (size_t)run); p += run; }
 									else { memset(p, '.', (size_t)run); p += run; }
@@ -1206,6 +1361,7 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 					}
 				}
 			});
+			tr("format", k, t0);
 			// Every file keeps input order: the part thread t formatted (reads [b_t, e_t) of the chunk) goes behind the parts
 			// of the threads before it.  The offsets follow from the buffer sizes, so all threads write at once with
 			// pwrite(), each its own (cache-warm) buffers, starting at a different file to stay off each other's inode locks.

@@ -273,6 +273,33 @@ def test_demux_read_only_architecture_matches_reference_cli(tmp_path):
     assert f"{st['num_EXTRACT_FAIL_LOW_COMPLEXITY']}\tlow complexity" in log
 
 
+@pytest.mark.parametrize("alpha", ["ACGTNacgtnRYKUu*-"])
+def test_demux_odd_characters_match_reference_cli(tmp_path, alpha):
+    """-1 R:N on one file whose reads hold lower-case bases, IUPAC letters, U and other characters: the writer's
+    sixteen-at-a-time base copy against the reference CLI's print_all, byte for byte (no GPU involved).  ('.' is left out:
+    the reference binary crashes on reads that contain it, with or without -Q.)"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    tmp = str(tmp_path)
+    rng = np.random.default_rng(21)
+    recs = []
+    for k in range(2500):
+        L = int(rng.integers(20, 140))
+        pool = list(alpha) if k % 3 == 0 else list("ACGT")
+        seq = "".join(rng.choice(pool, size=L))
+        recs.append((f"r{k} odd", seq, "".join(chr(int(c)) for c in rng.integers(33, 75, size=L))))
+    write_fastq(os.path.join(tmp, "r1.fq"), recs)
+    cpu = run_ref_cli(tmp, "-1 R:N r1.fq", "out")
+    mine = os.path.join(tmp, "mine"); os.makedirs(mine)
+    st = demux_run(None, [dict(path=os.path.join(tmp, "r1.fq"), model=None, num_read_segments=1)],
+                   os.path.join(mine, "out"), dust=100, threads=3, chunk_reads=600)
+    a = sorted(glob.glob(os.path.join(cpu, "out*.fq"))); b = sorted(glob.glob(os.path.join(mine, "out*.fq")))
+    assert [os.path.basename(x) for x in a] == [os.path.basename(x) for x in b] and len(a) >= 2
+    for x, y in zip(a, b):
+        assert filecmp.cmp(x, y, shallow=False), os.path.basename(x)
+    assert st["total_read"] == 2500
+
+
 def test_demux_unequal_files_error(tmp_path):
     rng = np.random.default_rng(1)
     recs = random_records(rng, 50, lo=30, hi=40)
