@@ -12,9 +12,12 @@
  * fixed-length Illumina run -- and re-opens every output file per chunk; with the HMM on the GPU
  * those two dominate the run time by orders of magnitude.
  *
- * Not covered here (the reference's own controller is called instead, found with
- * dlsym(RTLD_NEXT)): SAM/BAM input, TDG_REFERENCE_CONTROLLER=1.  The -ref artifact filter runs on the GPU
- * (k_artifact) inside the same streaming job; the reference's get_fasta() reads the sequences.
+ * SAM/BAM input (read by `samtools view` through the reference's io_handler / read_sam_chunk, which the streaming
+ * reader does not replace) takes a third route, chunk_loop() below: the reference's reader and print_all() around the
+ * GPU run_pHMM, chunk by chunk like the reference's loop but WITHOUT the per-read model rebuild -- the model is
+ * re-made at most once per chunk, and only when a read no longer fits it.  TDG_CONTROLLER=chunks forces that route for
+ * any input (tests).  TDG_REFERENCE_CONTROLLER=1 calls the reference's own controller (found with dlsym(RTLD_NEXT)).
+ * The -ref artifact filter runs on the GPU (k_artifact) on every route; the reference's get_fasta() reads the sequences.
  *
  * Documented differences, log file only: "Long sequence found. Need to realloc model..." is
  * written once with the number of reads it applies to instead of once per read, and the
@@ -75,11 +78,17 @@ static int ends_with(const char* s, const char* suf)
 	return a >= b && !strcmp(s + a - b, suf);
 }
 
-static int needs_reference_controller(struct parameters* param)
+static int needs_reference_controller(void)
+{
+	const char* e = getenv("TDG_REFERENCE_CONTROLLER");
+	return e && atoi(e);
+}
+
+static int needs_chunk_loop(struct parameters* param)
 {
 	int i;
-	const char* e = getenv("TDG_REFERENCE_CONTROLLER");
-	if (e && atoi(e)) return 1;
+	const char* e = getenv("TDG_CONTROLLER");
+	if (e && !strcmp(e, "chunks")) return 1;
 	for (i = 0; i < param->infiles; i++) {
 		const char* f = param->infile[i];
 		if (ends_with(f, ".sam") || ends_with(f, ".bam") || ends_with(f, ".sam.gz") || ends_with(f, ".bam.gz")) return 1;
@@ -87,11 +96,132 @@ static int needs_reference_controller(struct parameters* param)
 	return 0;
 }
 
+/* The reference's chunk loop (barcode_hmm.c:216-432) with its own reader (read_sam_chunk / read_fasta_fastq through
+ * io_handler) and writer (print_all), run_pHMM / run_rna_dust being the GPU definitions of run_phmm_gpu.c.  What is
+ * different: a read at least as long as the longest one before it (:293-309) is counted, and the model is re-made once
+ * per chunk only if such a read no longer fits its dynamic-programming length (the tables do not depend on that length). */
+static int chunk_loop(struct parameters* param, struct sequence_stats_info** ssi, struct model_bag** bags, char* read_present, long long barcode_present)
+{
+	const int nf = param->infiles;
+	int i, j, c, status = kslOK;
+	long long long_events = 0;
+	int total_read = 0, n_ok = 0, n_bar = 0, n_short = 0, n_arch = 0, n_art = 0, n_low = 0;
+	struct fasta* reference_fasta = NULL;
+	FILE** files = calloc(nf, sizeof *files);
+	struct read_info*** ric = calloc(nf, sizeof *ric);
+	int* numseqs = calloc(nf, sizeof(int));
+	int (*reader)(struct read_info**, struct parameters*, FILE*, int*) = NULL;
+
+	if (param->reference_fasta) {   /* :208-215 */
+		reference_fasta = get_fasta(reference_fasta, param->reference_fasta);
+		if (!reference_fasta) { status = kslFAIL; goto OUT; }
+		reference_fasta->mer_hash = calloc(reference_fasta->numseq > 0 ? reference_fasta->numseq : 1, sizeof(int));
+	}
+	for (i = 0; i < nf; i++) {
+		ric[i] = malloc_read_info(ric[i], param->num_query);
+		files[i] = io_handler(files[i], i, param);
+	}
+	reader = param->sam == 0 ? &read_fasta_fastq : &read_sam_chunk;
+	phase("chunk loop starts");
+	for (;;) {
+		c = 0;
+		for (i = 0; i < nf; i++) {
+			if (reader(ric[i], param, files[i], &numseqs[i]) != kslOK) {
+				snprintf(param->errmsg, kslibERRBUFSIZE, "Failed to read data chunk from file: %s", param->infile[i]);
+				status = kslFAIL; goto OUT;
+			}
+			c += numseqs[i];
+		}
+		if (!c) break;
+		for (i = 0; i < nf - 1; i++)
+			for (j = i + 1; j < nf; j++)
+				if (numseqs[i] != numseqs[j]) { say(param, "Input File:%s and %s differ in number of entries.\n", param->infile[i], param->infile[j]); die(param); }
+		if (!total_read)   /* :271-287 */
+			for (i = 0; i < nf - 1; i++)
+				for (j = i + 1; j < nf; j++)
+					for (c = 0; c < (numseqs[0] < 1000 ? numseqs[0] : 1000); c++)
+						if (compare_read_names(param, ric[i][c]->name, ric[j][c]->name)) {
+							say(param, "Files seem to contain reads in different order:\n%s\n%s\n", ric[i][c]->name, ric[j][c]->name);
+							die(param);
+						}
+		for (i = 0; i < nf; i++) {
+			for (j = 0; j < numseqs[0]; j++)
+				if (ric[i][j]->len >= ssi[i]->max_seq_len) { ssi[i]->max_seq_len = ric[i][j]->len; long_events++; }
+			if (ssi[i]->max_seq_len + 10 > bags[i]->current_dyn_length) {   /* init_model_bag sizes for max_seq_len + 10 (:5778) */
+				param->read_structure = param->read_structures[i];
+				free_model_bag(bags[i]);
+				bags[i] = init_model_bag(param, ssi[i]);
+			}
+		}
+		for (i = 0; i < nf; i++) {
+			param->read_structure = param->read_structures[i];
+			param->confidence_threshold = param->confidence_thresholds[i];
+			if (param->read_structure->num_segments == 1 && param->read_structure->type[0] == 'R') {
+				if (run_rna_dust(ric[i], param, reference_fasta, numseqs[i]) != kslOK) { snprintf(param->errmsg, kslibERRBUFSIZE, "run_rna_dust failed\n"); status = kslFAIL; goto OUT; }
+			} else {
+				if (run_pHMM(0, bags[i], ric[i], param, reference_fasta, numseqs[i], MODE_GET_LABEL) != kslOK) { status = kslFAIL; goto OUT; }
+			}
+		}
+		for (i = 0; i < nf; i++)   /* :329-341 */
+			if (barcode_present & (1 << i)) {
+				param->read_structure = param->read_structures[i];
+				if (i) for (j = 0; j < numseqs[0]; j++) ric[0][j]->barcode = ric[i][j]->barcode;
+				break;
+			}
+		for (i = 0; i < numseqs[0]; i++) {
+			c = -100000;
+			for (j = 0; j < nf; j++) if (ric[j][i]->read_type > c) c = ric[j][i]->read_type;
+			ric[0][i]->read_type = c;
+		}
+		print_all(ric, param, numseqs[0], read_present);
+		total_read += numseqs[0];
+		for (i = 0; i < numseqs[0]; i++)   /* :358-382 */
+			switch ((int)ric[0][i]->read_type) {
+				case EXTRACT_SUCCESS: n_ok++; break;
+				case EXTRACT_FAIL_BAR_FINGER_NOT_FOUND: n_bar++; break;
+				case EXTRACT_FAIL_READ_TOO_SHORT: n_short++; break;
+				case EXTRACT_FAIL_ARCHITECTURE_MISMATCH: n_arch++; break;
+				case EXTRACT_FAIL_MATCHES_ARTIFACTS: n_art++; n_low++; break;   /* falls through in the reference */
+				case EXTRACT_FAIL_LOW_COMPLEXITY: n_low++; break;
+				default:
+					n_art++;
+					if (reference_fasta) reference_fasta->mer_hash[((int)(ric[0][i]->read_type) >> 8) - 1]++;
+					break;
+			}
+	}
+	phase("chunk loop done");
+	if (long_events)
+		say(param, "Long sequence found. Need to realloc model... (%lld reads at least as long as the longest seen before; the GPU model does not depend on the read length)\n",
+		    long_events);
+	say(param, "Done.\n\n");
+	for (i = 0; i < nf; i++) say(param, "%s	Input file %d.\n", param->infile[i], i);
+	say(param, "%d	total input reads\n", total_read);
+	say(param, "%0.2f	selected threshold\n", param->confidence_threshold);
+	say(param, "%d	successfully extracted\n", n_ok);
+	say(param, "%0.1f%%	extracted\n", (float)n_ok / (float)total_read * 100.0f);
+	say(param, "%d	problems with architecture\n", n_arch);
+	say(param, "%d	barcode / UMI not found\n", n_bar);
+	say(param, "%d	too short\n", n_short);
+	say(param, "%d	low complexity\n", n_low);
+	say(param, "%d	match artifacts:\n", n_art);
+	if (reference_fasta)
+		for (i = 0; i < reference_fasta->numseq; i++)
+			if (reference_fasta->mer_hash[i]) say(param, "%d	%s\n", reference_fasta->mer_hash[i], reference_fasta->sn[i]);
+OUT:
+	if (reference_fasta) free_fasta(reference_fasta);
+	for (i = 0; i < nf; i++) {
+		if (ric[i]) free_read_info(ric[i], param->num_query);
+		if (files[i]) pclose(files[i]);
+	}
+	free(files); free(ric); free(numseqs);
+	return status;
+}
+
 int hmm_controller_multiple(struct parameters* param)
 {
 	const int nf = param->infiles;
 	int i, j, status = kslOK;
-	if (needs_reference_controller(param)) {
+	if (needs_reference_controller()) {
 		controller_fn ref = (controller_fn)dlsym(RTLD_NEXT, "hmm_controller_multiple");
 		if (!ref) { fprintf(stderr, "tagdust_b200: reference controller not found\n"); return kslFAIL; }
 		return ref(param);
@@ -178,6 +308,10 @@ int hmm_controller_multiple(struct parameters* param)
 	}
 
 	phase("thresholds and models done");
+	if (needs_chunk_loop(param)) {
+		status = chunk_loop(param, ssi, bags, read_present, barcode_present);
+		goto DONE;
+	}
 	/* ---- read-name order check of the first chunk (:271-287) on the first 1000 entries of every file */
 	if (nf > 1) {
 		struct read_info*** head = calloc(nf, sizeof *head);

@@ -1,9 +1,9 @@
-# usage: bash scripts/r02_scale8.sh <tag> [files_reads]  -- bench at 8 GPUs and at 1 GPU on the same box (strong-scaling file job with stage trace)
+# usage: bash scripts/r02_scale8.sh <tag> [files_reads] ["8 1"]  -- bench at 8 GPUs and at 1 GPU on the same box (strong-scaling file job with stage trace)
 cd /root/repo
-TAG=${1:-r02s8}; FR=${2:-32000000}
+TAG=${1:-r02s8}; FR=${2:-32000000}; NS=${3:-8 1}
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l; nproc; free -g | head -2 | tail -1; df -h /dev/shm | tail -1
-for n in 8 1; do
+for n in $NS; do
 	if [ $n -gt 1 ]; then
 		TDG_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --steps 5 --warmup 3 --files-reads $FR > gpurun_out/${TAG}_n$n.json 2> gpurun_out/${TAG}_n$n.err
 	else

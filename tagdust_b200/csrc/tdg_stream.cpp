@@ -1050,17 +1050,19 @@ extern "C" int tdg_demux_run(tdg_context* ctx, const tdg_demux_job* job, tdg_dem
 	Queue<int> q_free, q_conv, q_gpu, q_write;
 	for (int k = 0; k < NSLOT; k++) q_free.push(k);
 	Shared sh;
-	// Pinned staging is slow to create (page pinning runs at ~1 GB/s and is serialised per process), so the slots' batches
-	// are made one after the other on a set-up thread and every slot is released to the pipeline as soon as its own batch
-	// exists: chunk 0 is on the GPU while the staging of slots 1 and 2 is still being pinned.  (A longer read later on
-	// re-creates the batch of that slot.)  The scratch arenas (tens of GB per device) are allocated meanwhile.
+	// Staging batches are slow to create (pinning the host pages, then buffers, a stream and events on every device:
+	// 45-90 ms per batch on an 8-GPU box), so the slots' batches are made on set-up threads -- three at a time, slot k on
+	// thread k mod 3 -- and every slot is released to the pipeline as soon as its own batch exists: chunk 0 is on the GPU
+	// while the staging of later slots is still being pinned.  (A longer read later on re-creates the batch of that slot.)
+	// The scratch arenas (tens of GB per device) are allocated meanwhile.
 	std::vector<std::thread> t_alloc;
 	std::mutex ready_mu;
 	std::condition_variable ready_cv;
 	std::vector<char> slot_ready((size_t)NSLOT, 0);
 	bool scratch_ready = false;
-	t_alloc.emplace_back([&] {
-		for (int k = 0; k < NSLOT; k++) {
+	const int n_alloc = std::min(3, NSLOT);
+	for (int a = 0; a < n_alloc; a++) t_alloc.emplace_back([&, a] {
+		for (int k = a; k < NSLOT; k += n_alloc) {
 			for (int i = 0; i < NI && !sh.failed; i++) {
 				if (!((job->inputs[i].model || job->refset) && (job->inputs[i].expected_len > 0 || job->inputs[i].max_seq_len > 0))) continue;
 				const double ta = now_s();

@@ -254,6 +254,41 @@ def test_ref_artifact_filter_cli(tmp_path, threads):
     assert any("contaminant_" in line for line in gpu_log), "no artifact was counted: the test set is too easy"
 
 
+@pytest.mark.parametrize("ref", [False, True])
+def test_chunk_loop_route_matches_reference(tmp_path, ref):
+    """The route SAM/BAM input takes (integration/controller_gpu.c chunk_loop: the reference's reader and print_all around
+    the GPU run_pHMM, no per-read model rebuild), forced on FASTQ files with TDG_CONTROLLER=chunks because samtools is not
+    in this image.  All reads have the same length -- the case in which the reference's own loop rebuilds the model for
+    every read -- and the -t 1000-read chunks of the rtest build make several chunks."""
+    import time
+    tmp = str(tmp_path)
+    rng = np.random.default_rng(77)
+    make_fastq(os.path.join(tmp, "r1.fq"), 3300, [("R", None), ("B", TAGS)], seed=51, read_len=(72, 72), short=False)
+    make_fastq(os.path.join(tmp, "r2.fq"), 3300, [("R", None)], seed=52, read_len=(64, 64), short=False, name_fmt="M1:7:FC:1:{t}:{x}:{y} 2:N:0:1")
+    extra = ""
+    if ref:
+        write_reference_fasta(os.path.join(tmp, "contaminants.fa"), [os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")], rng)
+        extra = "-ref contaminants.fa -fe 2 "
+    outs, secs = {}, {}
+    for tag, binary in (("cpu", os.path.join(REF, "tagdust_rtest")), ("gpu", "TDG_CONTROLLER=chunks TDG_VERBOSE=1 " + GPU_BIN)):
+        d = os.path.join(tmp, tag)
+        os.makedirs(d, exist_ok=True)
+        t0 = time.time()
+        r = subprocess.run(f"{binary} -seed 42 -t 4 {extra}-1 R:N -2 {BARC} r1.fq r2.fq -o {d}/out", cwd=tmp, shell=True, capture_output=True, text=True)
+        secs[tag] = time.time() - t0
+        assert r.returncode == 0, f"{tag}: {r.stdout}\n{r.stderr}"
+        if tag == "gpu":
+            assert "chunk loop starts" in r.stderr, "the run did not take the chunk-loop route"
+        outs[tag] = d
+    a = sorted(glob.glob(os.path.join(outs["cpu"], "out*.fq")))
+    b = sorted(glob.glob(os.path.join(outs["gpu"], "out*.fq")))
+    assert [os.path.basename(x) for x in a] == [os.path.basename(x) for x in b] and a
+    for x, y in zip(a, b):
+        assert filecmp.cmp(x, y, shallow=False), f"{os.path.basename(x)} differs"
+    assert summary_lines(f"{outs['cpu']}/out_logfile.txt") == summary_lines(f"{outs['gpu']}/out_logfile.txt")
+    print(f"chunk-loop route: reference {secs['cpu']:.1f} s, drop-in {secs['gpu']:.1f} s")
+
+
 def test_streaming_on_two_devices_matches_one(tmp_path):
     """tdg_demux_run over a 2-GPU context (every chunk sharded contiguously over the devices) writes the
     same bytes as over one GPU."""
