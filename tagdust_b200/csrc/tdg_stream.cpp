@@ -149,18 +149,21 @@ void parallel_for(int threads, size_t n, size_t grain, F fn)
 	if (grain > 0) T = (int)std::min<size_t>(T, std::max<size_t>(1, n / grain));
 	if (T <= 1) { fn((size_t)0, n, 0); return; }
 	const size_t per = (n + T - 1) / T;
+	// a part that runs out of memory on a worker must not take the process down: the caller gets the exception
+	std::atomic<bool> oom{false};
+	const std::function<void(int)> part = [&](int t) {
+		try { fn(std::min(n, per * (size_t)t), std::min(n, per * (size_t)(t + 1)), t); }
+		catch (const std::bad_alloc&) { oom.store(true); }
+	};
 	if (tl_pool) {
-		const std::function<void(int)> part = [&](int t) { fn(std::min(n, per * (size_t)t), std::min(n, per * (size_t)(t + 1)), t); };
 		tl_pool->run(T, part);
-		return;
+	} else {
+		std::vector<std::thread> th;
+		for (int t = 1; t < T; t++) th.emplace_back([&part, t] { part(t); });
+		part(0);
+		for (auto& x : th) x.join();
 	}
-	std::vector<std::thread> th;
-	for (int t = 1; t < T; t++) {
-		const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
-		th.emplace_back([=] { fn(b, e, t); });
-	}
-	fn((size_t)0, std::min(n, per), 0);
-	for (auto& x : th) x.join();
+	if (oom.load()) throw std::bad_alloc();
 }
 
 struct NucTable {
