@@ -7,6 +7,7 @@
 //
 //   A  thread per read: 148 CTAs x 512 threads; HMM-outer, position-inner; the silent row cs[i] is read-modify-written
 //      through global memory once per HMM (like k_backward), 12 state registers.
+//   C  (below, added after B's result) one warp per HMM with 32 reads per warp, one CTA per 32 reads.
 //   B  warp per read: lane = HMM (49 HMMs = two rounds of 32 lanes, 15 lanes idle in the second), position loop serial;
 //      the ordered 49-term fold of a position is NOT on the recurrence's critical path (the HMMs read the NEXT segment's
 //      silent row), so it is done afterwards for 32 positions at once, lane = position, from a [HMM][position] tile in
@@ -133,6 +134,54 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_warp(const float* tabg, const
 	}
 }
 
+// ---- C: one warp per HMM, 32 reads per warp, one CTA per group of 32 reads ("thread per (read, HMM)")
+// No idle lanes (lane = read, as in A) and no silent-state traffic (as in B): the 49 HMMs of a segment run as 25 warps of
+// one CTA (warp w: HMMs w and w + 25), every warp walks the positions of its HMMs in blocks of 25 and leaves the
+// contributions in a [HMM][position][read] tile in shared memory; after a barrier warp p folds position p of the block
+// (lane = read, the 49 terms in order), after a second barrier the next block starts.  12-24 state registers per thread.
+constexpr int CW = 25, PB = 25;
+__global__ void __launch_bounds__(CW * 32, 1) k_cta(const float* tabg, const float* emg, const uint8_t* seq, const float* ps, float* cs, Model m, int reads)
+{
+	extern __shared__ float smem[];
+	float* tabs = smem;
+	float* ems = smem + 16000;
+	float* tile = ems + H * (NC + 1) * 4 + 12;   // [HMM][PB][32 reads]
+	for (int i = threadIdx.x; i < 16000; i += blockDim.x) tabs[i] = tabg[i];
+	for (int i = threadIdx.x; i < H * (NC + 1) * 4; i += blockDim.x) ems[i] = emg[i];
+	__syncthreads();
+	const TabAddr tab = (uint32_t)__cvta_generic_to_shared(tabs) - (0x4B000000u << 2);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int h0 = warp, h1 = warp + CW;
+	const bool two = h1 < H;
+	const float* em0 = ems + h0 * (NC + 1) * 4;
+	const float* em1 = ems + (two ? h1 : 0) * (NC + 1) * 4;
+	const size_t stride = (size_t)reads;   // arrays are [position][read], like A
+	for (size_t g = blockIdx.x; g * 32 < (size_t)reads; g += gridDim.x) {
+		const size_t r = g * 32 + lane;
+		float M0[NC], I0[NC], M1[NC], I1[NC];
+#pragma unroll
+		for (int c = 0; c < NC; ++c) { M0[c] = NEG; I0[c] = NEG; M1[c] = NEG; I1[c] = NEG; }
+		for (int ib = L; ib >= 1; ib -= PB) {
+			const int nb = ib >= PB ? PB : ib;
+			for (int p = 0; p < nb; ++p) {
+				const int i = ib - p;
+				const int x = seq[(size_t)i * stride + r];
+				const float pn = ps[(size_t)(i + 1) * stride + r];
+				tile[(h0 * PB + p) * 32 + lane] = hmm_step(M0, I0, em0, x, pn, m, tab);
+				if (two) tile[(h1 * PB + p) * 32 + lane] = hmm_step(M1, I1, em1, x, pn, m, tab);
+			}
+			__syncthreads();
+			if (warp < nb) {
+				float c0 = NEG;
+#pragma unroll 7
+				for (int h = 0; h < H; ++h) c0 = LS(c0, tile[(h * PB + warp) * 32 + lane], tab);
+				cs[(size_t)(ib - warp) * stride + r] = c0;
+			}
+			__syncthreads();
+		}
+	}
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
 int main()
@@ -169,6 +218,10 @@ int main()
 	const int smB = (16000 + H * (NC + 1) * 4 + 12 + WARPS * 64 * TP) * 4;
 	CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, smA));
 	CK(cudaFuncSetAttribute(k_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smB));
+	const int smC = (16000 + H * (NC + 1) * 4 + 12 + H * PB * 32) * 4;
+	CK(cudaFuncSetAttribute(k_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, smC));
+	std::vector<float> csC(cells);
+	float msC = 0;
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
 	std::vector<float> csA(cells), csB(cells);
@@ -189,6 +242,16 @@ int main()
 		CK(cudaEventSynchronize(e1));
 		cudaEventElapsedTime(&msB, e0, e1);
 		CK(cudaMemcpy(csB.data(), d_cs, cells * 4, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(d_cs, init.data(), cells * 4, cudaMemcpyHostToDevice));
+		cudaEventRecord(e0);
+		k_cta<<<148, CW * 32, smC>>>(d_tab, d_em, d_seq, d_ps, d_cs, m, READS);
+		cudaEventRecord(e1);
+		CK(cudaEventSynchronize(e1));
+		cudaEventElapsedTime(&msC, e0, e1);
+		CK(cudaMemcpy(csC.data(), d_cs, cells * 4, cudaMemcpyDeviceToHost));
+		size_t diffC = 0;
+		for (size_t i = (size_t)READS; i < (size_t)(L + 1) * READS; i++) diffC += memcmp(&csA[i], &csC[i], 4) != 0;
+		printf("rep %d: warp-per-HMM x 32 reads (one CTA per 32 reads) %.3f ms (x%.2f); silent rows differing: %zu\n", rep, msC, msC / msA, diffC);
 		size_t diff = 0;
 		for (size_t i = 1; i <= (size_t)L; i++)
 			for (size_t r = 0; r < (size_t)READS; r++) diff += memcmp(&csA[i * READS + r], &csB[r * (L + 2) + i], 4) != 0;
